@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""Benchmark of the descriptor-extraction hot path (BASELINE.json metric: point clouds/sec, global+local
+descriptors) - see the contract in DESIGN.md "Measurement".
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config cfg2] [--impl ours|reference]
+
+A step = one pass of the hot path over one batch of synthetic clouds (default: BASELINE config 2, batch=16
+KITTI-64-beam-shaped clouds, 0.10 m voxels, per GPU: weak scaling).
+  value : clouds/s with the voxelised batch already resident in HBM (egn_coords_build + egn_forward + top-256
+          keypoint selection), device-timed with CUDA events per step, L2 flushed between steps, max over ranks.
+  e2e   : same metric through the public API from pinned HOST point clouds: H2D of the raw points, GPU
+          quantisation, batching, forward, keypoint selection, D2H of global descriptors + top-256 keypoints
+          and their descriptors - all inside the timed region.
+  roofline     : dominant kernel class by device time (live CUDA-event brackets inside the engine).
+  cpu_baseline : the ME-semantics CPU oracle (oracle/, torch CPU, all host threads) on a bounded sample.
+--impl reference times that CPU oracle as the reference arm (MinkowskiEngine itself cannot be installed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+from egonn_b200 import synth  # noqa: E402
+
+TOPK = 256
+METRIC = "point clouds/sec (global+local desc)"
+UNIT = "clouds/s"
+
+
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_weights():
+    path = os.path.join(REPO, "tests", "golden", "egonn_weights.pth")
+    return torch.load(path, map_location="cpu", weights_only=True), "reference checkpoint (tests/golden/egonn_weights.pth)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_workload(cfg: str, batch: int, rank: int):
+    c = synth.CONFIGS[cfg]
+    first = (0 if cfg == "cfg1" else 1) + rank * batch
+    clouds = synth.make_batch(cfg, batch=batch, first_seed=first)
+    return clouds, c["voxel"], c["desc"]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    """Reference arm: the reference's forward restated on the CPU (oracle/, ME semantics) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import egonn_oracle, me_ops
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    sd, wdesc = load_weights()
+    clouds, voxel, desc = make_workload(args.config, 1, 0)
+    quant = {"coordinates": "cartesian", "step": voxel}
+    pc = torch.from_numpy(clouds[0])
+
+    def step():
+        c, _ = egonn_oracle.quantize(pc, quant)
+        bc = me_ops.batched_coordinates([c])
+        out = egonn_oracle.forward(sd, bc.numpy(), torch.ones((bc.shape[0], 1)), quant)
+        s = out["sigma"][:, 0]
+        idx = torch.topk(s, k=min(TOPK, s.shape[0]), largest=False).indices
+        return out["global"], out["keypoints"][idx], out["descriptors"][idx]
+
+    for _ in range(max(1, min(args.warmup, 1))):
+        step()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    value = 1.0 / dt
+    sample = f"{steps} step(s) of 1 cloud of {args.config} (quantise + forward + top-{TOPK}), torch CPU {cores} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": f"synthetic ({wdesc})",
+            "config": {"workload": f"{args.config}: {desc}; reference arm runs 1 cloud per step on the host CPU",
+                       "note": "ME-semantics CPU restatement (oracle/), not MinkowskiEngine: ME cannot be installed in this image"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--config", default="cfg2", choices=list(synth.CONFIGS))
+    ap.add_argument("--batch", type=int, default=None, help="clouds per GPU per step (default: the config's batch)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel-class table (JSON) here")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    import egonn_b200 as E
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(args.warmup, 3)
+    K = args.steps
+    batch = args.batch or synth.CONFIGS[args.config]["batch"]
+
+    sd, wdesc = load_weights()
+    clouds, voxel, desc = make_workload(args.config, batch, rank)
+    params = E.ModelParams.from_dict(model="egonn", coordinates="cartesian", quantization_step=voxel)
+    model = E.model_factory(params)
+    model.load_state_dict(sd)
+    model = model.eval().to(dev)
+
+    # ---- device-resident voxelised batch (the `value` arm) ----
+    coords = [params.quantizer(torch.from_numpy(pc).to(dev))[0] for pc in clouds]
+    bcoords = E.batched_coordinates(coords).contiguous()
+    feats = torch.ones((bcoords.shape[0], 1), device=dev)
+    gathered = torch.empty((world * batch, 256), device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # 256 MiB > 126 MB L2
+
+    def step_device():
+        p = model.forward_packed({"coords": bcoords, "features": feats})
+        idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, p["global"])
+        return p, idx
+
+    # ---- host-resident raw clouds (the `e2e` arm) ----
+    host_pts = [torch.from_numpy(pc).pin_memory() for pc in clouds]
+    h2d_bytes = sum(t.numel() * 4 for t in host_pts)
+    out_g = torch.empty((batch, 256), dtype=torch.float32).pin_memory()
+    out_kp = torch.empty((batch, TOPK, 3), dtype=torch.float32).pin_memory()
+    out_ds = torch.empty((batch, TOPK, 128), dtype=torch.float32).pin_memory()
+    d2h_bytes = (out_g.numel() + out_kp.numel() + out_ds.numel()) * 4
+
+    def step_e2e():
+        cs = []
+        for t in host_pts:
+            c, _ = params.quantizer(t.to(dev, non_blocking=True))
+            cs.append(c)
+        bc = E.batched_coordinates(cs)
+        f = torch.ones((bc.shape[0], 1), device=dev)
+        p = model.forward_packed({"coords": bc, "features": f})
+        idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK).long()
+        rows = (idx.clamp_min(0) + p["local_offsets"][:-1].long()[:, None])
+        out_g.copy_(p["global"], non_blocking=True)
+        out_kp.copy_(p["keypoints"][rows], non_blocking=True)
+        out_ds.copy_(p["descriptors"][rows], non_blocking=True)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, p["global"])
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    eng = None
+    for _ in range(W):
+        step_device()
+    eng = model._engine
+    barrier()
+
+    # ---- timed region: K steps, CUDA events per step, L2 flush between steps ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.zero_()
+        a.record()
+        step_device()
+        b.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = (eng.launch_count() - launches0) / K
+    dev_ms = [a.elapsed_time(b) for a, b in ev]
+    ms_step = float(np.sum(dev_ms) / K)
+
+    # ---- e2e arm ----
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        step_e2e()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+    clocks = sampler.stop()
+
+    # ---- per-kernel-class profile (separate pass so the event brackets do not perturb the timed region) ----
+    eng.profile(True)
+    for _ in range(min(K, 10)):
+        flush.zero_()
+        step_device()
+    torch.cuda.synchronize()
+    prof = eng.profile_read()
+    eng.profile(False)
+    n_prof = min(K, 10)
+
+    if world > 1:
+        t = torch.tensor([ms_step, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        total_ms = sum(e["ms"] for e in prof) or 1.0
+        top = max(prof, key=lambda e: e["ms"])
+        table = sorted(({"kernel": e["name"], "launches_per_step": e["launches"] / n_prof, "ms_per_step": e["ms"] / n_prof,
+                         "share": e["ms"] / total_ms, "alg_GBps": (e["alg_bytes"] / 1e9) / (e["ms"] / 1e3) if e["ms"] > 0 else None,
+                         "alg_bytes_per_launch": e["alg_bytes"] / max(e["launches"], 1),
+                         "GFLOPs": (e["flops"] / 1e9) / (e["ms"] / 1e3) if e["ms"] > 0 else None} for e in prof),
+                       key=lambda r: -r["ms_per_step"])
+        achieved = (top["alg_bytes"] / 1e9) / (top["ms"] / 1e3)
+        roofline = {"bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "share_of_step": top["ms"] / total_ms,
+                    "alg_bytes_per_launch": top["alg_bytes"] / max(top["launches"], 1),
+                    "avg_launch_ms": top["ms"] / max(top["launches"], 1)}
+        voxels = int(bcoords.shape[0])
+        line = {"metric": METRIC, "value": world * batch / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": f"synthetic ({wdesc})",
+                "config": {"workload": f"{args.config}: {desc}", "clouds_per_gpu": batch, "voxels_per_gpu_step": voxels,
+                           "level_rows": eng.info.n_rows[:8], "voxel_m": voxel, "topk": TOPK, "l2_flush_between_steps": True,
+                           "parallelism": f"dp{world} over clouds" + (", 1 NCCL all-gather of global descriptors" if world > 1 else "")},
+                "clocks": clocks,
+                "e2e": {"value": world * batch / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                        "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
+                "gpu_launches": launches, "wall_ms_per_step_incl_flush": t_wall * 1e3 / K,
+                "roofline": roofline}
+        if args.profile_out:
+            with open(args.profile_out, "w") as f:
+                json.dump({"kernels": table, "ms_per_step_profiled": total_ms / n_prof}, f, indent=1)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, sd)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, sd):
+    """The CPU oracle (ME-semantics restatement of the reference path) on a bounded sample, host cores of this box."""
+    from oracle import egonn_oracle, me_ops
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    clouds, voxel, _ = make_workload(args.config, 1, 0)
+    quant = {"coordinates": "cartesian", "step": voxel}
+    pc = torch.from_numpy(clouds[0])
+
+    def step():
+        c, _ = egonn_oracle.quantize(pc, quant)
+        bc = me_ops.batched_coordinates([c])
+        out = egonn_oracle.forward(sd, bc.numpy(), torch.ones((bc.shape[0], 1)), quant)
+        s = out["sigma"][:, 0]
+        torch.topk(s, k=min(TOPK, s.shape[0]), largest=False)
+
+    step()
+    n = 3
+    t0 = time.perf_counter()
+    for _ in range(n):
+        step()
+    dt = (time.perf_counter() - t0) / n
+    return {"value": 1.0 / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} runs of 1 cloud of {args.config} after 1 warm-up (quantise + forward + top-{TOPK}), torch CPU"}
+
+
+if __name__ == "__main__":
+    main()

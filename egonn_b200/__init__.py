@@ -1,0 +1,17 @@
+"""egonn_b200 - B200-native sparse-voxel descriptor extraction behind EgoNN's model_factory / MinkGL API.
+
+    from egonn_b200 import ModelParams, model_factory
+    params = ModelParams.from_dict(model="egonn", coordinates="cartesian", quantization_step=0.1)
+    model = model_factory(params).eval().cuda()
+    model.load_state_dict(torch.load("weights.pth"))
+    y = model({"coords": coords_cuda_int32_N4, "features": ones_cuda_N1})
+
+Everything that computes runs in hand-written sm_100a CUDA kernels behind the C ABI of
+``include/egonn_b200.h`` (``egonn_b200/csrc/libegonn_b200.so``).  There is no CPU fallback.
+"""
+from .params import ModelParams  # noqa: F401
+from .models import model_factory, create_egonn_model, MinkGL, MinkTrunk, MinkHead, ECABasicBlock  # noqa: F401
+from .quantization import CartesianQuantizer, PolarQuantizer, batched_coordinates  # noqa: F401
+from .engine import Engine, topk_smallest  # noqa: F401
+
+__version__ = "0.1.0"

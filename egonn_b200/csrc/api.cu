@@ -1,0 +1,240 @@
+// extern "C" surface of libegonn_b200.so (declared in include/egonn_b200.h) + context / arena plumbing.
+#include <stdarg.h>
+#include <string.h>
+
+#include "ctx.cuh"
+
+namespace egn {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int Arena::reserve(size_t bytes, cudaStream_t stream) {
+  used = 0;
+  if (bytes <= cap) return EGN_OK;
+  // grow: kernels enqueued earlier may still read the old block
+  EGN_CUDA(cudaStreamSynchronize(stream));
+  if (base) EGN_CUDA(cudaFree(base));
+  base = nullptr;
+  cap = 0;
+  size_t want = bytes + bytes / 4 + (1 << 20);
+  EGN_CUDA(cudaMalloc((void **)&base, want));
+  cap = want;
+  return EGN_OK;
+}
+void Arena::release() {
+  if (base) cudaFree(base);
+  base = nullptr;
+  cap = used = 0;
+}
+
+int Prof::begin(const char *name, double bytes, double flops, cudaStream_t s) {
+  int e = -1;
+  for (size_t i = 0; i < entries.size(); ++i)
+    if (strncmp(entries[i].name, name, sizeof(entries[i].name)) == 0) { e = (int)i; break; }
+  if (e < 0) {
+    egn_profile_entry pe;
+    memset(&pe, 0, sizeof(pe));
+    strncpy(pe.name, name, sizeof(pe.name) - 1);
+    entries.push_back(pe);
+    e = (int)entries.size() - 1;
+  }
+  entries[e].launches++;
+  entries[e].alg_bytes += bytes;
+  entries[e].flops += flops;
+  cudaEvent_t a = nullptr;
+  if (!pool.empty()) { a = pool.back(); pool.pop_back(); } else cudaEventCreate(&a);
+  cudaEventRecord(a, s);
+  cur = e;
+  cur_a = a;
+  return e;
+}
+void Prof::end(cudaStream_t s) {
+  if (cur < 0) return;
+  cudaEvent_t b = nullptr;
+  if (!pool.empty()) { b = pool.back(); pool.pop_back(); } else cudaEventCreate(&b);
+  cudaEventRecord(b, s);
+  pending.push_back({cur, cur_a, b});
+  cur = -1;
+  cur_a = nullptr;
+}
+int Prof::drain() {
+  for (auto &p : pending) {
+    cudaEventSynchronize(p.b);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) entries[p.entry].ms += ms;
+    pool.push_back(p.a);
+    pool.push_back(p.b);
+  }
+  pending.clear();
+  return EGN_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+}  // namespace egn
+
+using namespace egn;
+
+extern "C" {
+
+const char *egn_last_error(void) { return g_err; }
+int egn_version(void) { return 100; }
+
+int egn_ctx_create(egn_ctx **out, int device) {
+  EGN_CHECK(out != nullptr, EGN_ERR_INVALID, "ctx_create: null out");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  EGN_CHECK(e == cudaSuccess && count > 0, EGN_ERR_CUDA, "ctx_create: no CUDA device (%s) - this engine has no CPU path",
+            cudaGetErrorString(e));
+  EGN_CHECK(device >= 0 && device < count, EGN_ERR_INVALID, "ctx_create: device %d of %d", device, count);
+  DeviceGuard g(device);
+  cudaDeviceProp prop;
+  EGN_CUDA(cudaGetDeviceProperties(&prop, device));
+  EGN_CHECK(prop.major == 10, EGN_ERR_CUDA, "ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device,
+            prop.major, prop.minor);
+  egn_ctx *ctx = new egn_ctx();
+  ctx->device = device;
+  cudaError_t e1 = cudaMallocHost((void **)&ctx->host, sizeof(HostCounts));
+  cudaError_t e2 = cudaMalloc((void **)&ctx->dev_counts, sizeof(HostCounts));
+  if (e1 != cudaSuccess || e2 != cudaSuccess) {
+    set_error("ctx_create: allocation failed");
+    delete ctx;
+    return EGN_ERR_CUDA;
+  }
+  *out = ctx;
+  return EGN_OK;
+}
+
+int egn_ctx_destroy(egn_ctx *ctx) {
+  if (!ctx) return EGN_OK;
+  DeviceGuard g(ctx->device);
+  cudaDeviceSynchronize();
+  ctx->scratch.release();
+  ctx->coords.release();
+  ctx->feats.release();
+  ctx->prof.drain();
+  for (auto e : ctx->prof.pool) cudaEventDestroy(e);
+  if (ctx->host) cudaFreeHost(ctx->host);
+  if (ctx->dev_counts) cudaFree(ctx->dev_counts);
+  delete ctx;
+  return EGN_OK;
+}
+
+int egn_quantize(egn_ctx *ctx, const float *points, int64_t n, const float step[3], int polar, int32_t *coords_out,
+                 int64_t *index_out, int64_t *n_out, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return quantize(ctx, points, n, step, polar, coords_out, index_out, n_out, (cudaStream_t)stream);
+}
+
+int egn_coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n, egn_coords_info *info, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return coords_build(ctx, coords, n, info, (cudaStream_t)stream);
+}
+
+int egn_coords_get(egn_ctx *ctx, int level, int32_t *out, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return coords_get(ctx, level, out, (cudaStream_t)stream);
+}
+
+int egn_coords_input_rows(egn_ctx *ctx, int32_t *out, egn_stream_t stream) {
+  EGN_CHECK(ctx && ctx->pyr.valid && out, EGN_ERR_STATE, "coords_input_rows before coords_build");
+  DeviceGuard g(ctx->device);
+  EGN_CUDA(cudaMemcpyAsync(out, ctx->pyr.perm0, (size_t)ctx->pyr.n[0] * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return EGN_OK;
+}
+
+int egn_coords_batch_offsets(egn_ctx *ctx, int level, int32_t *out, egn_stream_t stream) {
+  EGN_CHECK(ctx && ctx->pyr.valid && out, EGN_ERR_STATE, "coords_batch_offsets before coords_build");
+  EGN_CHECK(level >= 0 && level < P, EGN_ERR_INVALID, "bad level");
+  DeviceGuard g(ctx->device);
+  EGN_CUDA(cudaMemcpyAsync(out, ctx->pyr.boff[level], (size_t)(ctx->pyr.n_batches + 1) * 4, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return EGN_OK;
+}
+
+int egn_coords_neighbors(egn_ctx *ctx, int level, int32_t *out, egn_stream_t stream) {
+  EGN_CHECK(ctx && ctx->pyr.valid && out, EGN_ERR_STATE, "coords_neighbors before coords_build");
+  EGN_CHECK(level >= 1 && level < P, EGN_ERR_INVALID, "neighbour tables exist for levels 1..%d", P - 1);
+  DeviceGuard g(ctx->device);
+  EGN_CUDA(cudaMemcpyAsync(out, ctx->pyr.nbr[level], (size_t)ctx->pyr.n[level] * 27 * 4, cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return EGN_OK;
+}
+
+int egn_forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float *features, float *global_out,
+                float *desc_out, float *keypoints_out, float *sigma_out, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return forward(ctx, net, weights, features, global_out, desc_out, keypoints_out, sigma_out, (cudaStream_t)stream);
+}
+
+int egn_forward_tap(egn_ctx *ctx, int which, int level, float *out, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return forward_tap(ctx, which, level, out, (cudaStream_t)stream);
+}
+
+int egn_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const float *w,
+             const float *scale, const float *shift, int relu, int accumulate, float *out, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return op_conv(ctx, level_in, ksize, transposed, cin, cout, in, w, scale, shift, relu, accumulate, out, (cudaStream_t)stream);
+}
+
+int egn_global_pool(egn_ctx *ctx, int level, int c, const float *in, int is_max, float *out, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return op_global_pool(ctx, level, c, in, is_max ? 2 : 0, 1.f, 0.f, out, (cudaStream_t)stream);
+}
+
+int egn_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const float *gate, float *out, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return op_broadcast_mul(ctx, level, c, in, gate, out, (cudaStream_t)stream);
+}
+
+int egn_profile_enable(egn_ctx *ctx, int enable) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  ctx->prof.on = enable != 0;
+  return EGN_OK;
+}
+
+int egn_profile_read(egn_ctx *ctx, egn_profile_entry *out, int capacity, int *n_out, int reset) {
+  EGN_CHECK(ctx && out && n_out, EGN_ERR_INVALID, "profile_read: null argument");
+  DeviceGuard g(ctx->device);
+  ctx->prof.drain();
+  const int n = (int)ctx->prof.entries.size();
+  EGN_CHECK(n <= capacity, EGN_ERR_CAPACITY, "profile_read: %d entries, capacity %d", n, capacity);
+  for (int i = 0; i < n; ++i) out[i] = ctx->prof.entries[i];
+  *n_out = n;
+  if (reset) ctx->prof.entries.clear();
+  return EGN_OK;
+}
+
+int64_t egn_launch_count(egn_ctx *ctx) { return ctx ? ctx->prof.launches : 0; }
+
+int egn_topk_smallest(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out, egn_stream_t stream) {
+  return op_topk(sigma, offsets, n_batches, k, idx_out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,599 @@
+// Coordinate pyramid ("coordinate manager") of the engine: voxel quantisation, Morton keys, one radix sort,
+// all strided levels in one pass, parent/child links and 27-neighbour tables without any hash table.
+//
+// Replaces (reference file:line under /root/reference):
+//   ME.utils.sparse_quantize           datasets/quantization.py:42,83      -> quantize()
+//   ME.SparseTensor(coords) hash build models/minkgl.py:269                -> coords_build() level 0
+//   stride-2 coordinate maps           models/minkgl.py:104-105,145-146    -> coords_build() levels 1..
+//   3^3 / 2^3 kernel maps              layers/eca_block.py:59-64, models/minkgl.py:39,145 -> nbr tables, cstart/cmask
+//
+// Design: keys are (batch | Morton(z,y,x)); after ONE sort every coarser level is a run-length compaction of
+// level 0 (parent key = key >> 3), so level L row indices are prefix counts of "new run at level L" flags and
+// the child->parent map, the first-child pointer and the 8-bit child occupancy fall out of the same pass.
+// Neighbour tables are built top-down: the neighbours of a voxel are children of its parent's neighbours.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "ctx.cuh"
+
+namespace egn {
+
+constexpr int kTileThreads = 256;
+constexpr int kTileSteps = 8;                                  // 32-element steps per warp
+constexpr int kTile = kTileThreads * kTileSteps;               // 2048 keys per block
+constexpr int kWarpsPerTile = kTileThreads / 32;
+
+// ------------------------------------------------------------------------------------------------------
+// pack (b,x,y,z) -> key, validate
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_pack_keys(const int4 *__restrict__ coords, int n, uint64_t *__restrict__ keys,
+                            uint32_t *__restrict__ vals, int *__restrict__ dev_counts /* [P]=n_batches, [P+1]=status */) {
+  int bmax = 0, bad = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int4 c = coords[i];
+    const bool ok = c.x >= 0 && c.x < kMaxBatch && c.y >= -kAxisBias && c.y < kAxisBias && c.z >= -kAxisBias &&
+                    c.z < kAxisBias && c.w >= -kAxisBias && c.w < kAxisBias;
+    if (!ok) {
+      bad = 1;
+      c = make_int4(0, 0, 0, 0);
+    }
+    bmax = max(bmax, c.x + 1);
+    keys[i] = make_key(0, (uint32_t)c.x, (uint32_t)(c.y + kAxisBias), (uint32_t)(c.z + kAxisBias),
+                       (uint32_t)(c.w + kAxisBias));
+    vals[i] = (uint32_t)i;
+  }
+  bmax = __reduce_max_sync(0xffffffffu, bmax);
+  bad = __reduce_max_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0) {
+    if (bmax) atomicMax(&dev_counts[P], bmax);
+    if (bad) atomicOr(&dev_counts[P + 1], 1);
+  }
+}
+
+// height of element i: the highest pyramid level at which it starts a new run (-1: duplicate of i-1)
+__device__ __forceinline__ int key_height(const uint64_t *__restrict__ keys, int i, int n) {
+  if (i >= n) return -1;
+  if (i == 0) return P - 1;
+  const uint64_t d = keys[i] ^ keys[i - 1];
+  if (d == 0) return -1;
+  const int h = (63 - __clzll((long long)d)) / 3;
+  return h < P - 1 ? h : P - 1;
+}
+
+// counts[L * nblocks + blk] = number of level-L rows that start inside this tile
+__global__ void __launch_bounds__(kTileThreads) k_level_count(const uint64_t *__restrict__ keys, int n, int nblocks,
+                                                              int *__restrict__ counts) {
+  __shared__ int s_cnt[P];
+  if (threadIdx.x < P) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int base = blockIdx.x * kTile + warp * (32 * kTileSteps);
+  int cnt[P];
+#pragma unroll
+  for (int L = 0; L < P; ++L) cnt[L] = 0;
+#pragma unroll
+  for (int s = 0; s < kTileSteps; ++s) {
+    const int h = key_height(keys, base + s * 32 + lane, n);
+#pragma unroll
+    for (int L = 0; L < P; ++L) cnt[L] += __popc(__ballot_sync(0xffffffffu, h >= L));
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int L = 0; L < P; ++L) atomicAdd(&s_cnt[L], cnt[L]);
+  }
+  __syncthreads();
+  if (threadIdx.x < P) counts[threadIdx.x * nblocks + blockIdx.x] = s_cnt[threadIdx.x];
+}
+
+// exclusive scan of counts along blocks for every level (single block), totals -> dev_counts[0..P)
+__global__ void __launch_bounds__(1024) k_level_scan(int *__restrict__ counts, int nblocks, int *__restrict__ dev_counts) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int L = 0; L < P; ++L) {
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    int *row = counts + (size_t)L * nblocks;
+    for (int start = 0; start < nblocks; start += 1024) {
+      const int i = start + threadIdx.x;
+      const int v = i < nblocks ? row[i] : 0;
+      int x = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      if (lane == 31) s_warp[warp] = x;
+      __syncthreads();
+      if (warp == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int y = __shfl_up_sync(0xffffffffu, w, o);
+          if (lane >= o) w += y;
+        }
+        s_warp[lane] = w;
+      }
+      __syncthreads();
+      const int carry = s_carry;
+      const int incl = x + (warp ? s_warp[warp - 1] : 0) + carry;
+      if (i < nblocks) row[i] = incl - v;
+      __syncthreads();
+      if (threadIdx.x == 1023) s_carry = incl;
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) dev_counts[L] = s_carry;
+    __syncthreads();
+  }
+}
+
+struct LevelPtrs {
+  uint64_t *keys[P];
+  int *up[P];
+  int *cstart[P];
+  uint32_t *cmask[P];
+  int *perm0;
+  unsigned long long *mask64;
+  int *first0;
+};
+
+__global__ void __launch_bounds__(kTileThreads) k_level_emit(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                             int n, int nblocks, const int *__restrict__ base, LevelPtrs out) {
+  __shared__ int s_wc[kWarpsPerTile][P];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int first = blockIdx.x * kTile + warp * (32 * kTileSteps);
+  const uint32_t lt = (1u << lane) - 1u;
+  int h[kTileSteps];
+  int run[P];
+#pragma unroll
+  for (int L = 0; L < P; ++L) run[L] = 0;
+#pragma unroll
+  for (int s = 0; s < kTileSteps; ++s) {
+    h[s] = key_height(keys, first + s * 32 + lane, n);
+#pragma unroll
+    for (int L = 0; L < P; ++L) run[L] += __popc(__ballot_sync(0xffffffffu, h[s] >= L));
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int L = 0; L < P; ++L) s_wc[warp][L] = run[L];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int L = 0; L < P; ++L) {
+    int b = base[(size_t)L * nblocks + blockIdx.x];
+    for (int w = 0; w < warp; ++w) b += s_wc[w][L];
+    run[L] = b;
+  }
+#pragma unroll
+  for (int s = 0; s < kTileSteps; ++s) {
+    const int i = first + s * 32 + lane;
+    const int hh = h[s];
+    int e[P], c[P];
+#pragma unroll
+    for (int L = 0; L < P; ++L) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, hh >= L);
+      e[L] = run[L] + __popc(bal & lt);
+      c[L] = e[L] + (hh >= L ? 1 : 0);
+      run[L] += __popc(bal);
+    }
+    if (hh >= 0) {
+      const uint64_t key = keys[i];
+      out.perm0[e[0]] = (int)vals[i];
+#pragma unroll
+      for (int L = 0; L < P; ++L) {
+        if (hh >= L) {
+          out.keys[L][e[L]] = key >> (3 * L);
+          if (L + 1 < P) out.up[L][e[L]] = c[L + 1] - 1;
+          if (L >= 1) out.cstart[L][e[L]] = e[L - 1];
+        }
+        if (L >= 1 && hh >= L - 1) atomicOr(&out.cmask[L][c[L] - 1], 1u << (uint32_t)((key >> (3 * (L - 1))) & 7ull));
+      }
+      atomicOr(&out.mask64[c[2] - 1], 1ull << (key & 63ull));
+      if (hh >= 2) out.first0[e[2]] = e[0];
+    }
+  }
+}
+
+// boff[L][b] = first row of batch b at level L (b = 0..n_batches)
+struct BoffArgs {
+  const uint64_t *keys[P];
+  int *boff[P];
+  int n[P];
+};
+__global__ void k_batch_offsets(BoffArgs a, int n_batches) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int L = t / (n_batches + 1), b = t % (n_batches + 1);
+  if (L >= P) return;
+  const uint64_t target = (uint64_t)b << (kMortonBits - 3 * L);
+  int lo = 0, hi = a.n[L];
+  const uint64_t *k = a.keys[L];
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (k[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  a.boff[L][b] = lo;
+}
+
+// 27-neighbour table of the coarsest level by binary search (a few hundred rows per cloud)
+__global__ void k_nbr_top(const uint64_t *__restrict__ keys, int n, int level, int *__restrict__ nbr) {
+  const int64_t total = (int64_t)n * 27;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(t / 27), k = (int)(t % 27);
+    uint32_t b, vx, vy, vz;
+    split_key(level, keys[r], b, vx, vy, vz);
+    const int lim = 1 << (kAxisBits - level);
+    const int nx = (int)vx + (k % 3) - 1, ny = (int)vy + (k / 3) % 3 - 1, nz = (int)vz + k / 9 - 1;
+    int res = -1;
+    if (nx >= 0 && nx < lim && ny >= 0 && ny < lim && nz >= 0 && nz < lim) {
+      const uint64_t q = make_key(level, b, (uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
+      int lo = 0, hi = n;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (keys[mid] < q) lo = mid + 1; else hi = mid;
+      }
+      if (lo < n && keys[lo] == q) res = lo;
+    }
+    nbr[t] = res;
+  }
+}
+
+// level L from level L+1: neighbour (c + d) lives in the parent's neighbour (or the parent itself) as the
+// child with code c' ; child row = cstart + popc(mask below c').
+__global__ void k_nbr_down(const uint64_t *__restrict__ keys, const int *__restrict__ up, int n,
+                           const int *__restrict__ nbr_up, const int *__restrict__ cstart_up,
+                           const uint32_t *__restrict__ cmask_up, int *__restrict__ nbr) {
+  const int64_t total = (int64_t)n * 27;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(t / 27), k = (int)(t % 27);
+    const uint32_t code = (uint32_t)(keys[r] & 7ull);
+    const int p = up[r];
+    const int px = (int)(code & 1u) + (k % 3) - 1, py = (int)((code >> 1) & 1u) + (k / 3) % 3 - 1,
+              pz = (int)((code >> 2) & 1u) + k / 9 - 1;
+    const int kk = ((px >> 1) + 1) + 3 * ((py >> 1) + 1) + 9 * ((pz >> 1) + 1);
+    const int q = kk == 13 ? p : nbr_up[(int64_t)p * 27 + kk];
+    int res = -1;
+    if (q >= 0) {
+      const uint32_t cc = (uint32_t)(px & 1) | ((uint32_t)(py & 1) << 1) | ((uint32_t)(pz & 1) << 2);
+      const uint32_t m = cmask_up[q];
+      if ((m >> cc) & 1u) res = cstart_up[q] + __popc(m & ((1u << cc) - 1u));
+    }
+    nbr[t] = res;
+  }
+}
+
+__global__ void k_decode_coords(const uint64_t *__restrict__ keys, int n, int level, int4 *__restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    uint32_t b, vx, vy, vz;
+    split_key(level, keys[i], b, vx, vy, vz);
+    out[i] = make_int4((int)b, (int)(vx << level) - kAxisBias, (int)(vy << level) - kAxisBias,
+                       (int)(vz << level) - kAxisBias);
+  }
+}
+
+// profile mode only: number of present (out,in) pairs of a neighbour table / of the conv0 window
+__global__ void k_count_pairs27(const int *__restrict__ nbr, int64_t total, unsigned long long *__restrict__ out) {
+  unsigned long long c = 0;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) c += nbr[t] >= 0;
+  c = __reduce_add_sync(0xffffffffu, (unsigned)c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+// conv0 pairs: for every level-2 cell, every voxel of the 5^3-dilated... counted exactly by brute force on bits:
+// pairs = sum over ordered voxel pairs (a,b) with |a-b|_inf <= R; one warp per level-0 row, same walk as k_conv0.
+__global__ void k_count_pairs_conv0(const uint64_t *__restrict__ keys0, const int *__restrict__ up0, const int *__restrict__ up1,
+                                    const int *__restrict__ nbr2, const uint64_t *__restrict__ mask64, int n0, int KS,
+                                    unsigned long long *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int KV = KS * KS * KS, R = KS / 2;
+  unsigned long long total = 0;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n0; r += warps) {
+    const uint32_t m = (uint32_t)(keys0[r] & 63ull);
+    const int lx = (m & 1) | ((m >> 2) & 2), ly = ((m >> 1) & 1) | ((m >> 3) & 2), lz = ((m >> 2) & 1) | ((m >> 4) & 2);
+    const int cell = up1[up0[r]];
+    unsigned long long occ = 0ull;
+    if (lane < 27) {
+      const int q = nbr2[(int64_t)cell * 27 + lane];
+      if (q >= 0) occ = mask64[q];
+    }
+    const uint32_t occ_lo = (uint32_t)occ, occ_hi = (uint32_t)(occ >> 32);
+    for (int t0 = 0; t0 < KV; t0 += 32) {
+      const int t = t0 + lane, tt = t < KV ? t : 0;
+      const int px = lx + (tt % KS) - R, py = ly + (tt / KS) % KS - R, pz = lz + tt / (KS * KS) - R;
+      const int j = ((px >> 2) + 1) + 3 * ((py >> 2) + 1) + 9 * ((pz >> 2) + 1);
+      const uint32_t bit = (uint32_t)((px & 1) | ((py & 1) << 1) | ((pz & 1) << 2) | ((px & 2) << 2) | ((py & 2) << 3) | ((pz & 2) << 4));
+      const uint32_t lo = __shfl_sync(0xffffffffu, occ_lo, j), hi = __shfl_sync(0xffffffffu, occ_hi, j);
+      const unsigned long long o = ((unsigned long long)hi << 32) | lo;
+      total += __popc(__ballot_sync(0xffffffffu, t < KV && ((o >> bit) & 1ull)));
+    }
+  }
+  if (lane == 0 && total) atomicAdd(out, total);
+}
+
+// ------------------------------------------------------------------------------------------------------
+static int sort_pairs(Arena &scratch, uint64_t *kin, uint64_t *kout, uint32_t *vin, uint32_t *vout, int n, int end_bit,
+                      cudaStream_t s) {
+  size_t temp_bytes = 0;
+  EGN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, kin, kout, vin, vout, n, 0, end_bit, s));
+  void *temp = scratch.take(temp_bytes);
+  EGN_CHECK(temp != nullptr, EGN_ERR_STATE, "scratch arena exhausted in sort_pairs");
+  EGN_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, n, 0, end_bit, s));
+  return EGN_OK;
+}
+
+static size_t sort_scratch_bytes(int64_t n) {
+  // keys in/out, vals in/out, cub temp (onesweep: histograms + a few KB; bound generously), tile counts
+  const int64_t nblocks = div_up(n, kTile);
+  return pad256(n * 8) * 2 + pad256(n * 4) * 2 + pad256(n * 1 + (1 << 20)) + pad256(nblocks * P * 4) + (1 << 16);
+}
+
+int coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n64, egn_coords_info *info, cudaStream_t s) {
+  EGN_CHECK(ctx && coords && info, EGN_ERR_INVALID, "coords_build: null argument");
+  EGN_CHECK(n64 > 0 && n64 < (int64_t)1 << 26, EGN_ERR_INVALID, "coords_build: n=%lld out of range (1..2^26)", (long long)n64);
+  EGN_CHECK(((uintptr_t)coords & 15) == 0, EGN_ERR_INVALID, "coords_build: coords must be 16-byte aligned");
+  const int n = (int)n64;
+  Pyramid &py = ctx->pyr;
+  py = Pyramid();
+  const int nblocks = (int)div_up(n, kTile);
+
+  Arena &sc = ctx->scratch;
+  EGN_TRY(sc.reserve(sort_scratch_bytes(n), s));
+  uint64_t *kin = (uint64_t *)sc.take((size_t)n * 8), *kout = (uint64_t *)sc.take((size_t)n * 8);
+  uint32_t *vin = (uint32_t *)sc.take((size_t)n * 4), *vout = (uint32_t *)sc.take((size_t)n * 4);
+  int *counts = (int *)sc.take((size_t)nblocks * P * 4);
+  EGN_CHECK(kin && kout && vin && vout && counts, EGN_ERR_STATE, "scratch arena exhausted");
+
+  EGN_CUDA(cudaMemsetAsync(ctx->dev_counts, 0, sizeof(HostCounts), s));
+  EGN_LAUNCH(ctx, "coords_pack_keys", (double)n * 28, 0, s,
+             k_pack_keys<<<grid_for(n, 256), 256, 0, s>>>((const int4 *)coords, n, kin, vin, ctx->dev_counts));
+  if (ctx->prof.on) ctx->prof.begin("coords_radix_sort(cub)", (double)n * 24 * 8, 0, s);
+  EGN_TRY(sort_pairs(sc, kin, kout, vin, vout, n, 64, s));
+  if (ctx->prof.on) ctx->prof.end(s);
+  EGN_LAUNCH(ctx, "coords_level_count", (double)n * 8, 0, s, k_level_count<<<nblocks, kTileThreads, 0, s>>>(kout, n, nblocks, counts));
+  EGN_LAUNCH(ctx, "coords_level_scan", (double)nblocks * P * 8, 0, s, k_level_scan<<<1, 1024, 0, s>>>(counts, nblocks, ctx->dev_counts));
+  EGN_CUDA(cudaMemcpyAsync(ctx->host, ctx->dev_counts, sizeof(HostCounts), cudaMemcpyDeviceToHost, s));
+  EGN_CUDA(cudaStreamSynchronize(s));
+
+  const HostCounts &hc = *ctx->host;
+  info->n_input = n;
+  info->n_batches = hc.n_batches;
+  info->status = hc.status ? EGN_ERR_RANGE : EGN_OK;
+  for (int L = 0; L < P; ++L) info->n_rows[L] = hc.totals[L];
+  EGN_CHECK(hc.status == 0, EGN_ERR_RANGE,
+            "coords_build: coordinate outside [-2^17, 2^17) or batch index outside [0, 1023)");
+
+  // exact-size pyramid storage
+  const int B = hc.n_batches;
+  size_t need = 0;
+  for (int L = 0; L < P; ++L) {
+    const size_t m = (size_t)hc.totals[L];
+    need += pad256(m * 8) + 3 * pad256(m * 4) + pad256(m * 27 * 4) + pad256((size_t)(B + 1) * 4);
+  }
+  need += pad256((size_t)hc.totals[0] * 4) + pad256((size_t)hc.totals[2] * 8) + pad256((size_t)hc.totals[2] * 4) + 4096;
+  Arena &ca = ctx->coords;
+  EGN_TRY(ca.reserve(need, s));
+  LevelPtrs lp;
+  for (int L = 0; L < P; ++L) {
+    const size_t m = (size_t)hc.totals[L];
+    py.n[L] = hc.totals[L];
+    py.keys[L] = lp.keys[L] = (uint64_t *)ca.take(m * 8);
+    py.up[L] = lp.up[L] = (int *)ca.take(m * 4);
+    py.cstart[L] = lp.cstart[L] = (int *)ca.take(m * 4);
+    py.cmask[L] = lp.cmask[L] = (uint32_t *)ca.take(m * 4);
+    py.nbr[L] = L >= 1 ? (int *)ca.take(m * 27 * 4) : nullptr;
+    py.boff[L] = (int *)ca.take((size_t)(B + 1) * 4);
+    EGN_CHECK(py.keys[L] && py.up[L] && py.cstart[L] && py.cmask[L] && py.boff[L] && (L == 0 || py.nbr[L]),
+              EGN_ERR_STATE, "coords arena exhausted");
+    if (L >= 1) EGN_CUDA(cudaMemsetAsync(py.cmask[L], 0, m * 4, s));
+  }
+  py.perm0 = lp.perm0 = (int *)ca.take((size_t)hc.totals[0] * 4);
+  py.mask64 = (uint64_t *)ca.take((size_t)hc.totals[2] * 8);
+  lp.mask64 = (unsigned long long *)py.mask64;
+  py.first0 = lp.first0 = (int *)ca.take((size_t)hc.totals[2] * 4);
+  EGN_CHECK(py.perm0 && py.mask64 && py.first0, EGN_ERR_STATE, "coords arena exhausted");
+  EGN_CUDA(cudaMemsetAsync(py.mask64, 0, (size_t)hc.totals[2] * 8, s));
+
+  {
+    double b = (double)n * 12;
+    for (int L = 0; L < P; ++L) b += (double)py.n[L] * 20;
+    EGN_LAUNCH(ctx, "coords_level_emit", b, 0, s, k_level_emit<<<nblocks, kTileThreads, 0, s>>>(kout, vout, n, nblocks, counts, lp));
+  }
+
+  BoffArgs ba;
+  for (int L = 0; L < P; ++L) {
+    ba.keys[L] = py.keys[L];
+    ba.boff[L] = py.boff[L];
+    ba.n[L] = py.n[L];
+  }
+  EGN_LAUNCH(ctx, "coords_batch_offsets", (double)P * (B + 1) * 4, 0, s,
+             k_batch_offsets<<<(int)div_up((int64_t)P * (B + 1), 128), 128, 0, s>>>(ba, B));
+
+  // kernel-map build: algorithmic bytes N*8 (keys) + N*27*4 (table) per level
+  const int T = P - 1;
+  EGN_LAUNCH(ctx, "kernel_map_3x3x3", (double)py.n[T] * (8 + 108), 0, s,
+             k_nbr_top<<<grid_for((int64_t)py.n[T] * 27, 256), 256, 0, s>>>(py.keys[T], py.n[T], T, py.nbr[T]));
+  for (int L = T - 1; L >= 1; --L)
+    EGN_LAUNCH(ctx, "kernel_map_3x3x3", (double)py.n[L] * (8 + 108), 0, s,
+               k_nbr_down<<<grid_for((int64_t)py.n[L] * 27, 256), 256, 0, s>>>(py.keys[L], py.up[L], py.n[L], py.nbr[L + 1],
+                                                                                 py.cstart[L + 1], py.cmask[L + 1], py.nbr[L]));
+  EGN_CUDA(cudaGetLastError());
+  py.n_input = n;
+  py.n_batches = B;
+  py.valid = true;
+
+  if (ctx->prof.on) {  // pair counts for the algorithmic-byte model (not part of the product path)
+    unsigned long long *cnt = (unsigned long long *)sc.take((P + 1) * 8);
+    EGN_CHECK(cnt != nullptr, EGN_ERR_STATE, "scratch arena exhausted");
+    EGN_CUDA(cudaMemsetAsync(cnt, 0, (P + 1) * 8, s));
+    for (int L = 1; L < P; ++L)
+      if (py.n[L]) k_count_pairs27<<<grid_for((int64_t)py.n[L] * 27, 256), 256, 0, s>>>(py.nbr[L], (int64_t)py.n[L] * 27, cnt + L);
+    k_count_pairs_conv0<<<grid_for((int64_t)py.n[0] * 32, 256, 16), 256, 0, s>>>(py.keys[0], py.up[0], py.up[1], py.nbr[2], py.mask64,
+                                                                                  py.n[0], 5, cnt + P);
+    unsigned long long h[P + 1];
+    EGN_CUDA(cudaMemcpyAsync(h, cnt, (P + 1) * 8, cudaMemcpyDeviceToHost, s));
+    EGN_CUDA(cudaStreamSynchronize(s));
+    for (int L = 1; L < P; ++L) py.pairs27[L] = (long long)h[L];
+    py.pairs_conv0 = (long long)h[P];
+  }
+  return EGN_OK;
+}
+
+int coords_get(egn_ctx *ctx, int level, int32_t *out, cudaStream_t s) {
+  EGN_CHECK(ctx && ctx->pyr.valid, EGN_ERR_STATE, "coords_get before coords_build");
+  EGN_CHECK(level >= 0 && level < P && out, EGN_ERR_INVALID, "coords_get: bad level/out");
+  const int n = ctx->pyr.n[level];
+  if (n == 0) return EGN_OK;
+  EGN_LAUNCH(ctx, "coords_decode", (double)n * 24, 0, s, k_decode_coords<<<grid_for(n, 256), 256, 0, s>>>(ctx->pyr.keys[level], n, level, (int4 *)out));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// sparse_quantize: floor(p / q) -> int32, first occurrence wins, survivors in input order
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_quant_pack(const float *__restrict__ pts, int n, float q0, float q1, float q2, int polar,
+                             int *__restrict__ vox /* (n,3) */, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                             int *__restrict__ dev_counts) {
+  int bad = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+    float a, b, c;
+    if (polar) {
+      // datasets/quantization.py:35-41, f32 throughout: 180. + (atan2(y,x) * 180.) / np.pi, evaluated left to right
+      const float theta = __fadd_rn(180.f, __fdiv_rn(__fmul_rn(atan2f(y, x), 180.f), 3.14159265358979323846f));
+      const float dist = sqrtf(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
+      a = __fdiv_rn(theta, q0);
+      b = __fdiv_rn(dist, q1);
+      c = __fdiv_rn(z, q2);
+    } else if (q0 != 1.0f) {
+      a = __fdiv_rn(x, q0);
+      b = __fdiv_rn(y, q0);
+      c = __fdiv_rn(z, q0);
+    } else {
+      a = x; b = y; c = z;
+    }
+    const float fa = floorf(a), fb = floorf(b), fc = floorf(c);
+    const float lim = (float)kAxisBias;
+    const bool ok = fa >= -lim && fa < lim && fb >= -lim && fb < lim && fc >= -lim && fc < lim;  // also rejects NaN
+    int ia = 0, ib = 0, ic = 0;
+    if (ok) { ia = (int)fa; ib = (int)fb; ic = (int)fc; } else bad = 1;
+    vox[3 * (size_t)i] = ia; vox[3 * (size_t)i + 1] = ib; vox[3 * (size_t)i + 2] = ic;
+    keys[i] = make_key(0, 0u, (uint32_t)(ia + kAxisBias), (uint32_t)(ib + kAxisBias), (uint32_t)(ic + kAxisBias));
+    vals[i] = (uint32_t)i;
+  }
+  bad = __reduce_max_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicOr(&dev_counts[P + 1], 1);
+}
+
+// stable sort => the first element of every run of equal keys is the earliest input row
+__global__ void k_mark_first(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals, int n,
+                             uint8_t *__restrict__ keep) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (i == 0 || keys[i] != keys[i - 1]) keep[vals[i]] = 1;
+}
+__global__ void __launch_bounds__(kTileThreads) k_keep_count(const uint8_t *__restrict__ keep, int n, int *__restrict__ counts) {
+  int c = 0;
+  const int base = blockIdx.x * kTile;
+  for (int j = threadIdx.x; j < kTile; j += kTileThreads) c += (base + j < n) ? keep[base + j] : 0;
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ int s;
+  if (threadIdx.x == 0) s = 0;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) atomicAdd(&s, c);
+  __syncthreads();
+  if (threadIdx.x == 0) counts[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(1024) k_scan1(int *__restrict__ counts, int nblocks, int *__restrict__ total) {
+  __shared__ int s_warp[32];
+  __shared__ int s_carry;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int start = 0; start < nblocks; start += 1024) {
+    const int i = start + threadIdx.x;
+    const int v = i < nblocks ? counts[i] : 0;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = s_warp[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+      s_warp[lane] = w;
+    }
+    __syncthreads();
+    const int incl = x + (warp ? s_warp[warp - 1] : 0) + s_carry;
+    if (i < nblocks) counts[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = s_carry;
+}
+__global__ void __launch_bounds__(kTileThreads) k_keep_emit(const uint8_t *__restrict__ keep, const int *__restrict__ vox, int n,
+                                                            const int *__restrict__ base, int *__restrict__ coords_out,
+                                                            long long *__restrict__ index_out) {
+  __shared__ int s_wc[kWarpsPerTile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int first = blockIdx.x * kTile + warp * (32 * kTileSteps);
+  int f[kTileSteps], cnt = 0;
+#pragma unroll
+  for (int s = 0; s < kTileSteps; ++s) {
+    const int i = first + s * 32 + lane;
+    f[s] = i < n ? keep[i] : 0;
+    cnt += __popc(__ballot_sync(0xffffffffu, f[s]));
+  }
+  if (lane == 0) s_wc[warp] = cnt;
+  __syncthreads();
+  int run = base[blockIdx.x];
+  for (int w = 0; w < warp; ++w) run += s_wc[w];
+#pragma unroll
+  for (int s = 0; s < kTileSteps; ++s) {
+    const int i = first + s * 32 + lane;
+    const uint32_t bal = __ballot_sync(0xffffffffu, f[s]);
+    if (f[s]) {
+      const int o = run + __popc(bal & ((1u << lane) - 1u));
+      coords_out[3 * (size_t)o] = vox[3 * (size_t)i];
+      coords_out[3 * (size_t)o + 1] = vox[3 * (size_t)i + 1];
+      coords_out[3 * (size_t)o + 2] = vox[3 * (size_t)i + 2];
+      index_out[o] = i;
+    }
+    run += __popc(bal);
+  }
+}
+
+int quantize(egn_ctx *ctx, const float *points, int64_t n64, const float step[3], int polar, int32_t *coords_out,
+             int64_t *index_out, int64_t *n_out, cudaStream_t s) {
+  EGN_CHECK(ctx && points && step && coords_out && index_out && n_out, EGN_ERR_INVALID, "quantize: null argument");
+  EGN_CHECK(n64 > 0 && n64 < (int64_t)1 << 26, EGN_ERR_INVALID, "quantize: n out of range");
+  EGN_CHECK(step[0] > 0.f && (!polar || (step[1] > 0.f && step[2] > 0.f)), EGN_ERR_INVALID, "quantize: step must be > 0");
+  const int n = (int)n64;
+  const int nblocks = (int)div_up(n, kTile);
+  Arena &sc = ctx->scratch;
+  EGN_TRY(sc.reserve(sort_scratch_bytes(n) + pad256((size_t)n * 12) + pad256(n), s));
+  uint64_t *kin = (uint64_t *)sc.take((size_t)n * 8), *kout = (uint64_t *)sc.take((size_t)n * 8);
+  uint32_t *vin = (uint32_t *)sc.take((size_t)n * 4), *vout = (uint32_t *)sc.take((size_t)n * 4);
+  int *vox = (int *)sc.take((size_t)n * 12);
+  uint8_t *keep = (uint8_t *)sc.take((size_t)n);
+  int *counts = (int *)sc.take((size_t)nblocks * 4);
+  EGN_CHECK(kin && kout && vin && vout && vox && keep && counts, EGN_ERR_STATE, "scratch arena exhausted");
+  EGN_CUDA(cudaMemsetAsync(ctx->dev_counts, 0, sizeof(HostCounts), s));
+  EGN_CUDA(cudaMemsetAsync(keep, 0, (size_t)n, s));
+  EGN_LAUNCH(ctx, "quantize_pack", (double)n * 36, 0, s,
+             k_quant_pack<<<grid_for(n, 256), 256, 0, s>>>(points, n, step[0], step[1], step[2], polar, vox, kin, vin, ctx->dev_counts));
+  if (ctx->prof.on) ctx->prof.begin("quantize_radix_sort(cub)", (double)n * 24 * 7, 0, s);
+  EGN_TRY(sort_pairs(sc, kin, kout, vin, vout, n, kMortonBits, s));
+  if (ctx->prof.on) ctx->prof.end(s);
+  EGN_LAUNCH(ctx, "quantize_mark_first", (double)n * 13, 0, s, k_mark_first<<<grid_for(n, 256), 256, 0, s>>>(kout, vout, n, keep));
+  EGN_LAUNCH(ctx, "quantize_compact", (double)n * 2, 0, s, k_keep_count<<<nblocks, kTileThreads, 0, s>>>(keep, n, counts));
+  EGN_LAUNCH(ctx, "quantize_compact", 0, 0, s, k_scan1<<<1, 1024, 0, s>>>(counts, nblocks, ctx->dev_counts + P + 2));
+  EGN_LAUNCH(ctx, "quantize_compact", (double)n * 13, 0, s,
+             k_keep_emit<<<nblocks, kTileThreads, 0, s>>>(keep, vox, n, counts, coords_out, (long long *)index_out));
+  EGN_CUDA(cudaMemcpyAsync(ctx->host, ctx->dev_counts, sizeof(HostCounts), cudaMemcpyDeviceToHost, s));
+  EGN_CUDA(cudaStreamSynchronize(s));
+  EGN_CHECK(ctx->host->status == 0, EGN_ERR_RANGE, "quantize: voxel coordinate outside [-2^17, 2^17) (or NaN input)");
+  *n_out = ctx->host->n_out;
+  return EGN_OK;
+}
+
+}  // namespace egn

@@ -1,0 +1,101 @@
+// Engine context: coordinate pyramid ("coordinate manager") + scratch arenas.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace egn {
+
+constexpr int P = EGN_PYR_LEVELS;  // pyramid levels 0..P-1
+
+struct Pyramid {
+  bool valid = false;
+  int n_input = 0, n_batches = 0;
+  int n[P] = {0};
+  // per level L (device pointers into ctx->coords arena)
+  uint64_t *keys[P] = {nullptr};   // sorted level-L keys (level-0 key >> 3L)
+  int *up[P] = {nullptr};          // row at L -> parent row at L+1           (L < P-1)
+  int *cstart[P] = {nullptr};      // row at L -> first child row at L-1      (L >= 1)
+  uint32_t *cmask[P] = {nullptr};  // row at L -> 8-bit child occupancy       (L >= 1)
+  int *nbr[P] = {nullptr};         // (n[L],27) neighbour rows at L, -1 absent (L >= 1)
+  int *boff[P] = {nullptr};        // (n_batches+1) first row of each batch
+  int *perm0 = nullptr;            // canonical L0 row -> input row
+  uint64_t *mask64 = nullptr;      // per L2 cell: occupancy of its 4x4x4 level-0 voxels (bit = key0 & 63)
+  int *first0 = nullptr;           // per L2 cell: first level-0 row
+  long long pairs27[P] = {0};      // present (out,in) pairs of the 3^3 kernel map (profile mode only)
+  long long pairs_conv0 = 0;       // present pairs of the conv0 window (profile mode only)
+};
+
+struct HostCounts {  // pinned
+  int totals[P];
+  int n_batches;
+  int status;
+  int n_out;
+};
+
+// per-kernel-class event timing (bench.py's live roofline numbers)
+struct Prof {
+  bool on = false;
+  long long launches = 0;
+  struct Pending { int entry; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<egn_profile_entry> entries;
+  std::vector<cudaEvent_t> pool;
+  int begin(const char *name, double bytes, double flops, cudaStream_t s);
+  void end(cudaStream_t s);
+  int drain();
+  int cur = -1;
+  cudaEvent_t cur_a = nullptr;
+};
+
+struct Taps {  // device pointers of the last forward's feature maps (feature arena)
+  float *conv0 = nullptr;
+  float *down[EGN_MAX_LEVELS] = {nullptr};
+  float *block[EGN_MAX_LEVELS] = {nullptr};
+  int c_down[EGN_MAX_LEVELS] = {0}, c_block[EGN_MAX_LEVELS] = {0};
+  int c0 = 0;
+  float *gmap = nullptr, *lmap = nullptr;
+  int c_g = 0, c_l = 0, lvl_g = 0, lvl_l = 0;
+};
+
+}  // namespace egn
+
+struct egn_ctx {
+  int device = 0;
+  egn::Arena scratch;   // sort double-buffers, CUB temp, tile counts (dead after coords_build / quantize)
+  egn::Arena coords;    // pyramid
+  egn::Arena feats;     // feature maps of the running forward
+  egn::Pyramid pyr;
+  egn::HostCounts *host = nullptr;  // pinned
+  int *dev_counts = nullptr;        // device mirror of HostCounts
+  egn::Taps taps;
+  egn::Prof prof;
+};
+
+// bracket one kernel class: counts the launch, and in profile mode records start/stop events
+#define EGN_LAUNCH(ctx, name, bytes, flops, stream, ...)            \
+  do {                                                               \
+    (ctx)->prof.launches++;                                          \
+    if ((ctx)->prof.on) (ctx)->prof.begin(name, bytes, flops, stream); \
+    __VA_ARGS__;                                                     \
+    if ((ctx)->prof.on) (ctx)->prof.end(stream);                     \
+  } while (0)
+
+namespace egn {
+// coords.cu
+int coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n, egn_coords_info *info, cudaStream_t s);
+int coords_get(egn_ctx *ctx, int level, int32_t *out, cudaStream_t s);
+int quantize(egn_ctx *ctx, const float *points, int64_t n, const float step[3], int polar, int32_t *coords_out,
+             int64_t *index_out, int64_t *n_out, cudaStream_t s);
+// ops.cu
+int op_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const float *w,
+            const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s);
+int op_global_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, float p, float eps, float *out,
+                   cudaStream_t s);
+int op_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const float *g, float *out, cudaStream_t s);
+int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out, cudaStream_t s);
+// forward.cu
+int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float *features, float *global_out,
+            float *desc_out, float *kp_out, float *sigma_out, cudaStream_t s);
+int forward_tap(egn_ctx *ctx, int which, int level, float *out, cudaStream_t s);
+}  // namespace egn

@@ -1,0 +1,218 @@
+// Whole-network scheduler: MinkGL.forward (models/minkgl.py:267-315) / MinkLoc.forward (models/minkloc.py:44-61)
+// as one stream of kernels on the context's coordinate pyramid.  Feature maps live in the context's feature
+// arena (exact sizes - the level row counts are known on the host after coords_build).
+#include "ctx.cuh"
+
+namespace egn {
+
+// ops.cu
+int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const float *scale, const float *shift, int cout,
+              int relu, float *out, cudaStream_t s);
+int run_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const float *w,
+             const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s);
+int run_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, float p, float eps, float *part, int slices,
+             float *out, cudaStream_t s);
+int run_gather_rows1(egn_ctx *ctx, const float *in, const int *perm, int n, float *out, cudaStream_t s);
+int run_eca_gate(egn_ctx *ctx, int level, int c, const float *t, const float *wk, int k, float *part, int slices, float *gate,
+                 cudaStream_t s);
+int run_eca_apply(egn_ctx *ctx, int level, int c, const float *t, const float *res, const float *gate, int relu, float *out,
+                  cudaStream_t s);
+int run_l2norm(egn_ctx *ctx, const float *x, int n, int c, float *out, cudaStream_t s);
+int run_kp_sigma(egn_ctx *ctx, int level, const float *kp_raw, const float *sg_raw, int polar, const float q[3], int ignore_offset,
+                 float *kp_out, float *sg_out, cudaStream_t s);
+int pool_slices_for(egn_ctx *ctx, int level);
+
+namespace {
+
+struct Fwd {
+  egn_ctx *ctx;
+  const egn_net *net;
+  const float *wb;
+  cudaStream_t s;
+  const float *W(int64_t off) const { return off < 0 ? nullptr : wb + off; }
+  float *alloc(size_t floats) { return (float *)ctx->feats.take(floats * 4); }
+
+  // conv described by an egn_layer on the pyramid
+  int layer(const egn_layer &l, int level_in, int ksize, int transposed, const float *in, int relu, int accumulate, float *out) {
+    return run_conv(ctx, level_in, ksize, transposed, l.cin, l.cout, in, W(l.w), W(l.scale), W(l.shift), relu, accumulate, out, s);
+  }
+};
+
+size_t head_floats(const Pyramid &py, const egn_head &h) {
+  if (h.n_levels == 0) return 0;
+  size_t f = 0;
+  for (int L = h.levels[0]; L <= h.levels[h.n_levels - 1]; ++L) f += (size_t)py.n[L] * h.out_channels + 64;
+  return f;
+}
+
+size_t plan_floats(const Pyramid &py, const egn_net &net) {
+  size_t f = (size_t)py.n[0] + (size_t)py.n[0] * net.conv0.cout + 256;
+  for (int L = 1; L <= net.n_levels; ++L) {
+    const size_t n = py.n[L];
+    f += n * net.down[L].cout + 3 * n * net.conv2[L].cout + (net.res[L].cin ? n * net.res[L].cout : 0) + 512;
+    f += (size_t)py.n_batches * (64 + 1) * net.conv2[L].cout + 128;
+  }
+  f += head_floats(py, net.global_head) + head_floats(py, net.local_head);
+  if (net.global_head.n_levels) {
+    const size_t n = py.n[net.global_head.levels[0]];
+    f += n * (net.global_mlp[0].cin ? net.global_mlp[0].cout + net.global_mlp[1].cout : 0) + 256;
+    f += (size_t)py.n_batches * 64 * 512 + 256;
+  }
+  if (net.local_head.n_levels) {
+    const size_t n = py.n[net.local_head.levels[0]];
+    f += n * (net.desc_mlp[0].cout + net.desc_mlp[1].cout + net.kp_mlp[0].cout + net.kp_mlp[1].cout + net.sigma_mlp[0].cout +
+              net.sigma_mlp[1].cout) + 1024;
+  }
+  return f + 4096;
+}
+
+// MinkHead.forward (models/minkgl.py:46-60): y = conv1x1[hi](x[hi]); for level hi-1..lo: y = tconv[level+1](y) (+ conv1x1[level](x[level]))
+int run_head(Fwd &F, const egn_head &h, float *const x[], float **out_map) {
+  const Pyramid &py = F.ctx->pyr;
+  const int lo = h.levels[0], hi = h.levels[h.n_levels - 1];
+  float *y = F.alloc((size_t)py.n[hi] * h.out_channels);
+  EGN_CHECK(y != nullptr, EGN_ERR_STATE, "feature arena exhausted (head)");
+  EGN_TRY(F.layer(h.conv1x1[hi], hi, 1, 0, x[hi], 0, 0, y));
+  for (int level = hi - 1; level >= lo; --level) {
+    float *y2 = F.alloc((size_t)py.n[level] * h.out_channels);
+    EGN_CHECK(y2 != nullptr, EGN_ERR_STATE, "feature arena exhausted (head)");
+    EGN_TRY(F.layer(h.tconv[level + 1], level + 1, 2, 1, y, 0, 0, y2));
+    bool lateral = false;
+    for (int i = 0; i < h.n_levels; ++i) lateral |= (h.levels[i] == level);
+    if (lateral) EGN_TRY(F.layer(h.conv1x1[level], level, 1, 0, x[level], 0, 1, y2));
+    y = y2;
+  }
+  *out_map = y;
+  return EGN_OK;
+}
+
+}  // namespace
+
+int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float *features, float *global_out,
+            float *desc_out, float *kp_out, float *sigma_out, cudaStream_t s) {
+  EGN_CHECK(ctx && net && weights && features, EGN_ERR_INVALID, "forward: null argument");
+  Pyramid &py = ctx->pyr;
+  EGN_CHECK(py.valid, EGN_ERR_STATE, "forward before coords_build");
+  EGN_CHECK(net->n_levels >= 1 && net->n_levels < EGN_MAX_LEVELS && net->n_levels + 2 < P, EGN_ERR_INVALID, "forward: n_levels out of range");
+  EGN_CHECK(net->conv0.cin == 1, EGN_ERR_INVALID, "forward: conv0 expects one input channel (models/model_factory.py:13)");
+  const bool do_global = global_out != nullptr, do_local = desc_out || kp_out || sigma_out;
+  EGN_CHECK(!do_global || net->global_head.n_levels > 0, EGN_ERR_INVALID, "forward: model has no global head");
+  EGN_CHECK(!do_local || (net->local_head.n_levels > 0 && desc_out && kp_out && sigma_out), EGN_ERR_INVALID,
+            "forward: local outputs need a local head and all three buffers");
+
+  EGN_TRY(ctx->feats.reserve(plan_floats(py, *net) * 4, s));
+  Fwd F{ctx, net, weights, s};
+  Taps &tp = ctx->taps;
+  tp = Taps();
+
+  // ---- trunk (models/minkgl.py:136-153) ----
+  float *f0 = F.alloc(py.n[0]);
+  float *x0 = F.alloc((size_t)py.n[0] * net->conv0.cout);
+  EGN_CHECK(f0 && x0, EGN_ERR_STATE, "feature arena exhausted (conv0)");
+  EGN_TRY(run_gather_rows1(ctx, features, py.perm0, py.n[0], f0, s));
+  EGN_TRY(run_conv0(ctx, net->conv0_ksize, f0, F.W(net->conv0.w), F.W(net->conv0.scale), F.W(net->conv0.shift),
+                    net->conv0.cout, 1, x0, s));
+  tp.conv0 = x0;
+  tp.c0 = net->conv0.cout;
+
+  float *x[EGN_MAX_LEVELS] = {nullptr};
+  x[0] = x0;
+  const float *cur = x0;
+  for (int L = 1; L <= net->n_levels; ++L) {
+    const size_t n = py.n[L];
+    const int c = net->conv2[L].cout;
+    float *d = F.alloc(n * net->down[L].cout), *t1 = F.alloc(n * c), *t2 = F.alloc(n * c), *xo = F.alloc(n * c);
+    EGN_CHECK(d && t1 && t2 && xo, EGN_ERR_STATE, "feature arena exhausted (level %d)", L);
+    EGN_TRY(F.layer(net->down[L], L - 1, 2, 0, cur, 1, 0, d));              // convs[L] + bn[L] + relu
+    EGN_TRY(F.layer(net->conv1[L], L, 3, 0, d, 1, 0, t1));                  // conv1 + norm1 + relu
+    EGN_TRY(F.layer(net->conv2[L], L, 3, 0, t1, 0, 0, t2));                 // conv2 + norm2
+    const float *res = d;
+    if (net->res[L].cin) {                                                  // downsample: 1x1 + bn
+      float *r = F.alloc(n * c);
+      EGN_CHECK(r != nullptr, EGN_ERR_STATE, "feature arena exhausted (residual)");
+      EGN_TRY(F.layer(net->res[L], L, 1, 0, d, 0, 0, r));
+      res = r;
+    } else {
+      EGN_CHECK(net->down[L].cout == c, EGN_ERR_INVALID, "identity residual with a channel change at level %d", L);
+    }
+    const float *gate = nullptr;
+    if (net->eca_k[L] > 0) {                                                // ECALayer
+      const int slices = pool_slices_for(ctx, L);
+      float *part = F.alloc((size_t)py.n_batches * slices * c), *g = F.alloc((size_t)py.n_batches * c);
+      EGN_CHECK(part && g, EGN_ERR_STATE, "feature arena exhausted (eca)");
+      EGN_TRY(run_eca_gate(ctx, L, c, t2, F.W(net->eca_w[L]), net->eca_k[L], part, slices, g, s));
+      gate = g;
+    }
+    EGN_TRY(run_eca_apply(ctx, L, c, t2, res, gate, 1, xo, s));             // out = relu(eca(out) + residual)
+    x[L] = xo;
+    cur = xo;
+    tp.down[L] = d; tp.c_down[L] = net->down[L].cout;
+    tp.block[L] = xo; tp.c_block[L] = c;
+  }
+
+  // ---- global head -> decoder -> pooling (models/minkgl.py:273-286) ----
+  if (do_global) {
+    const egn_head &h = net->global_head;
+    float *gm = nullptr;
+    EGN_TRY(run_head(F, h, x, &gm));
+    const int lvl = h.levels[0];
+    int c = h.out_channels;
+    tp.gmap = gm; tp.c_g = c; tp.lvl_g = lvl;
+    const float *pin = gm;
+    if (net->global_mlp[0].cin) {
+      float *m1 = F.alloc((size_t)py.n[lvl] * net->global_mlp[0].cout), *m2 = F.alloc((size_t)py.n[lvl] * net->global_mlp[1].cout);
+      EGN_CHECK(m1 && m2, EGN_ERR_STATE, "feature arena exhausted (global mlp)");
+      EGN_TRY(F.layer(net->global_mlp[0], lvl, 1, 0, gm, 1, 0, m1));
+      EGN_TRY(F.layer(net->global_mlp[1], lvl, 1, 0, m1, 0, 0, m2));
+      pin = m2;
+      c = net->global_mlp[1].cout;
+    }
+    const int slices = pool_slices_for(ctx, lvl);
+    float *part = F.alloc((size_t)py.n_batches * slices * c);
+    EGN_CHECK(part != nullptr, EGN_ERR_STATE, "feature arena exhausted (pool)");
+    const int mode = net->pool_method == 0 ? 1 : (net->pool_method == 1 ? 0 : 2);
+    EGN_TRY(run_pool(ctx, lvl, c, pin, mode, net->gem_p, net->gem_eps, part, slices, global_out, s));
+  }
+
+  // ---- local head (models/minkgl.py:288-308) ----
+  if (do_local) {
+    const egn_head &h = net->local_head;
+    float *lm = nullptr;
+    EGN_TRY(run_head(F, h, x, &lm));
+    const int lvl = h.levels[0];
+    const size_t n = py.n[lvl];
+    tp.lmap = lm; tp.c_l = h.out_channels; tp.lvl_l = lvl;
+    float *d1 = F.alloc(n * net->desc_mlp[0].cout), *d2 = F.alloc(n * net->desc_mlp[1].cout);
+    float *k1 = F.alloc(n * net->kp_mlp[0].cout), *k2 = F.alloc(n * net->kp_mlp[1].cout);
+    float *s1 = F.alloc(n * net->sigma_mlp[0].cout), *s2 = F.alloc(n * net->sigma_mlp[1].cout);
+    EGN_CHECK(d1 && d2 && k1 && k2 && s1 && s2, EGN_ERR_STATE, "feature arena exhausted (local mlps)");
+    EGN_CHECK(net->kp_mlp[1].cout == 3 && net->sigma_mlp[1].cout == 1, EGN_ERR_INVALID, "keypoint/sigma regressor shapes");
+    EGN_TRY(F.layer(net->desc_mlp[0], lvl, 1, 0, lm, 1, 0, d1));
+    EGN_TRY(F.layer(net->desc_mlp[1], lvl, 1, 0, d1, 0, 0, d2));
+    EGN_TRY(run_l2norm(ctx, d2, (int)n, net->desc_mlp[1].cout, desc_out, s));
+    EGN_TRY(F.layer(net->kp_mlp[0], lvl, 1, 0, lm, 1, 0, k1));
+    EGN_TRY(F.layer(net->kp_mlp[1], lvl, 1, 0, k1, 0, 0, k2));
+    EGN_TRY(F.layer(net->sigma_mlp[0], lvl, 1, 0, lm, 1, 0, s1));
+    EGN_TRY(F.layer(net->sigma_mlp[1], lvl, 1, 0, s1, 0, 0, s2));
+    EGN_TRY(run_kp_sigma(ctx, lvl, k2, s2, net->polar, net->quant_step, net->ignore_keypoint_regressor, kp_out, sigma_out, s));
+  }
+  return EGN_OK;
+}
+
+int forward_tap(egn_ctx *ctx, int which, int level, float *out, cudaStream_t s) {
+  EGN_CHECK(ctx && out && ctx->pyr.valid, EGN_ERR_STATE, "forward_tap: no forward to tap");
+  const Pyramid &py = ctx->pyr;
+  const Taps &tp = ctx->taps;
+  const float *src = nullptr;
+  size_t floats = 0;
+  if (which == 0) { src = tp.conv0; floats = (size_t)py.n[0] * tp.c0; }
+  else if (which == 1 && level >= 1 && level < EGN_MAX_LEVELS) { src = tp.down[level]; floats = (size_t)py.n[level] * tp.c_down[level]; }
+  else if (which == 2 && level >= 1 && level < EGN_MAX_LEVELS) { src = tp.block[level]; floats = (size_t)py.n[level] * tp.c_block[level]; }
+  else if (which == 3) { src = tp.gmap; floats = (size_t)py.n[tp.lvl_g] * tp.c_g; }
+  else if (which == 4) { src = tp.lmap; floats = (size_t)py.n[tp.lvl_l] * tp.c_l; }
+  EGN_CHECK(src != nullptr, EGN_ERR_STATE, "forward_tap: tap %d/%d not available", which, level);
+  EGN_CUDA(cudaMemcpyAsync(out, src, floats * 4, cudaMemcpyDeviceToDevice, s));
+  return EGN_OK;
+}
+
+}  // namespace egn

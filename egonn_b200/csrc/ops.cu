@@ -1,0 +1,594 @@
+// Feature operators of the engine on the context's coordinate maps (FP32 CUDA-core path).
+//
+// Replaces (reference file:line under /root/reference; MinkowskiEngine semantics per SURVEY.md Appendix A):
+//   ME.MinkowskiConvolution k=5 (conv0)        models/minkgl.py:100-102,140-142   -> k_conv0
+//   ME.MinkowskiConvolution k=3 / k=2 s2 / k=1 models/minkgl.py:104-107,124-126, layers/eca_block.py:59-64 -> k_sconv
+//   ME.MinkowskiConvolutionTranspose k=2 s2    models/minkgl.py:39,52-53          -> k_sconv (parent gather)
+//   ME.MinkowskiBatchNorm (eval) / ReLU / Linear bias                              -> fused epilogue scale/shift/relu
+//   ME.MinkowskiGlobalPooling, BroadcastMultiplication, ECALayer  layers/eca_block.py:21-36 -> k_pool_partial, k_eca_gate, k_eca_apply
+//   GeM / SPoC / MAC                           layers/pooling.py:46-86            -> k_pool_partial + k_pool_final
+//
+// All convolutions are OUTPUT-STATIONARY: one CTA owns a tile of output rows, walks the kernel offsets,
+// gathers the input rows named by the neighbour table (absent -> zeros) and accumulates in registers; the
+// output row is written exactly once with the BatchNorm/ReLU/residual epilogue applied - no atomics, no
+// separate scatter pass, deterministic.
+#include "ctx.cuh"
+
+namespace egn {
+
+// ------------------------------------------------------------------------------------------------------
+// generic gathered convolution
+// ------------------------------------------------------------------------------------------------------
+enum GatherMode { G_IDENTITY = 0, G_NBR27 = 1, G_CHILD8 = 2, G_PARENT = 3 };
+
+struct ConvArgs {
+  const float *in;
+  float *out;
+  const float *w;      // (K, cin, cout)
+  const float *scale;  // (cout) or null
+  const float *shift;  // (cout) or null
+  int n_out, cin, cout, K, relu, accumulate, mode;
+  const int *nbr;          // G_NBR27: (n_out,27)
+  const int *cstart;       // G_CHILD8: per output row, first child (input row)
+  const uint32_t *cmask;   // G_CHILD8: per output row, child occupancy
+  const int *up;           // G_PARENT: per output (fine) row, parent (input) row
+  const uint64_t *keys;    // G_PARENT: per output row key (code = key & 7)
+};
+
+constexpr int TM = 64;   // output rows per CTA
+constexpr int KC = 32;   // input-channel chunk
+constexpr int APAD = 4;
+
+template <int TN>
+__global__ void __launch_bounds__(256) k_sconv(ConvArgs a) {
+  constexpr int RN = TN / 16;
+  __shared__ int s_idx[TM * 27];
+  __shared__ __align__(16) float s_a[TM][KC + APAD];
+  __shared__ __align__(16) float s_w[KC][TN];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int row0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  const int K = a.K;
+
+  // resolve the input row of every (tile row, offset)
+  for (int t = tid; t < TM * K; t += 256) {
+    const int r = t / K, k = t % K, row = row0 + r;
+    int src = -1;
+    if (row < a.n_out) {
+      if (a.mode == G_IDENTITY) src = row;
+      else if (a.mode == G_NBR27) src = a.nbr[(int64_t)row * 27 + k];
+      else if (a.mode == G_CHILD8) {
+        const uint32_t m = a.cmask[row];
+        if ((m >> k) & 1u) src = a.cstart[row] + __popc(m & ((1u << k) - 1u));
+      } else {
+        if ((int)(a.keys[row] & 7ull) == k) src = a.up[row];
+      }
+    }
+    s_idx[r * K + k] = src;
+  }
+  __syncthreads();
+
+  float acc[4][RN];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
+
+  const bool vec_a = (a.cin & 3) == 0;
+  const bool vec_w = (a.cout & 3) == 0 && n0 + TN <= a.cout;
+  for (int k = 0; k < K; ++k) {
+    const int present = (tid < TM) && (s_idx[tid * K + k] >= 0);
+    if (!__syncthreads_or(present)) continue;
+    const float *wk = a.w + (size_t)k * a.cin * a.cout;
+    for (int kc0 = 0; kc0 < a.cin; kc0 += KC) {
+      // gather A chunk: 8 threads per row, 4 floats each
+#pragma unroll
+      for (int pass = 0; pass < TM / 32; ++pass) {
+        const int r = pass * 32 + (tid >> 3), c = (tid & 7) * 4;
+        const int src = s_idx[r * K + k];
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src >= 0) {
+          const float *p = a.in + (size_t)src * a.cin + kc0 + c;
+          if (vec_a && kc0 + c + 3 < a.cin) v = *(const float4 *)p;
+          else {
+            if (kc0 + c < a.cin) v.x = p[0];
+            if (kc0 + c + 1 < a.cin) v.y = p[1];
+            if (kc0 + c + 2 < a.cin) v.z = p[2];
+            if (kc0 + c + 3 < a.cin) v.w = p[3];
+          }
+        }
+        *(float4 *)&s_a[r][c] = v;
+      }
+      // W chunk (KC x TN)
+      for (int t = tid; t < KC * TN / 4; t += 256) {
+        const int kk = t / (TN / 4), c = (t % (TN / 4)) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kc0 + kk < a.cin) {
+          const float *p = wk + (size_t)(kc0 + kk) * a.cout + n0 + c;
+          if (vec_w) v = *(const float4 *)p;
+          else {
+            if (n0 + c < a.cout) v.x = p[0];
+            if (n0 + c + 1 < a.cout) v.y = p[1];
+            if (n0 + c + 2 < a.cout) v.z = p[2];
+            if (n0 + c + 3 < a.cout) v.w = p[3];
+          }
+        }
+        *(float4 *)&s_w[kk][c] = v;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < KC; ++kk) {
+        float av[4], wv[RN];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = s_a[ty + 16 * i][kk];
+#pragma unroll
+        for (int j = 0; j < RN; ++j) wv[j] = s_w[kk][tx + 16 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+#pragma unroll
+  for (int j = 0; j < RN; ++j) {
+    const int col = n0 + tx + 16 * j;
+    if (col >= a.cout) continue;
+    const float sc = a.scale ? a.scale[col] : 1.f, sh = a.shift ? a.shift[col] : 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = row0 + ty + 16 * i;
+      if (row >= a.n_out) continue;
+      float v = acc[i][j] * sc + sh;
+      if (a.relu) v = fmaxf(v, 0.f);
+      float *o = a.out + (size_t)row * a.cout + col;
+      if (a.accumulate) v += *o;
+      *o = v;
+    }
+  }
+}
+
+// pairs = number of (in,out) row pairs the convolution touches (SURVEY 8d byte model)
+static int launch_sconv(egn_ctx *ctx, const ConvArgs &a, long long pairs, cudaStream_t s) {
+  if (a.n_out <= 0) return EGN_OK;
+  const int gx = (int)div_up(a.n_out, TM);
+  char name[48];
+  static const char *kind[] = {"rowmm", "conv3x3x3", "conv2x2x2s2", "tconv2x2x2s2"};
+  snprintf(name, sizeof(name), "%s_c%d_%d", kind[a.mode], a.cin, a.cout);
+  const double bytes = a.mode == G_IDENTITY ? (double)pairs * (a.cin + a.cout) * 4
+                                            : (double)pairs * (a.cin + a.cout) * 4 + (double)pairs * 8 + (double)a.K * a.cin * a.cout * 4;
+  const double flops = 2.0 * pairs * a.cin * a.cout;
+  if (a.cout <= 32) EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv<32><<<dim3(gx, 1), 256, 0, s>>>(a));
+  else if (a.cout <= 64) EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv<64><<<dim3(gx, 1), 256, 0, s>>>(a));
+  else EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv<128><<<dim3(gx, (int)div_up(a.cout, 128)), 256, 0, s>>>(a));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// conv0: 5x5x5, Cin = 1 -> out[o] = sum_k f[o + d_k] * W[k,:]: a masked sum of kernel rows, not a GEMM.
+// One warp per level-0 row.  The 5^3 window of a voxel lies inside the 3x3x3 block of level-2 cells (4^3
+// voxels each) around its own cell; presence = one bit of that cell's 64-bit occupancy word, row = first
+// row of the cell + popcount of the lower bits.  No hash probes: 27 coalesced table reads per row.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t morton6(int x, int y, int z) {  // x,y,z in [0,4)
+  return (uint32_t)((x & 1) | ((y & 1) << 1) | ((z & 1) << 2) | ((x & 2) << 2) | ((y & 2) << 3) | ((z & 2) << 4));
+}
+
+template <int KS>
+__global__ void __launch_bounds__(256) k_conv0(const float *__restrict__ f0 /* (n0) canonical order */, const uint64_t *__restrict__ keys0,
+                                               const int *__restrict__ up0, const int *__restrict__ up1, const int *__restrict__ nbr2,
+                                               const uint64_t *__restrict__ mask64, const int *__restrict__ first0, int n0,
+                                               const float *__restrict__ w /* (KS^3,1,cout) */, const float *__restrict__ scale,
+                                               const float *__restrict__ shift, int cout, int relu, float *__restrict__ out) {
+  constexpr int KV = KS * KS * KS, R = KS / 2, ROUNDS = (KV + 31) / 32;
+  extern __shared__ float s_w0[];  // KV * cout
+  for (int t = threadIdx.x; t < KV * cout; t += blockDim.x) s_w0[t] = w[t];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n0; r += warps) {
+    const uint32_t m = (uint32_t)(keys0[r] & 63ull);
+    const int lx = (m & 1) | ((m >> 2) & 2), ly = ((m >> 1) & 1) | ((m >> 3) & 2), lz = ((m >> 2) & 1) | ((m >> 4) & 2);
+    const int cell = up1[up0[r]];
+    // lanes 0..26 hold the occupancy word / first row of the 27 neighbouring level-2 cells
+    unsigned long long occ = 0ull;
+    int base = 0;
+    if (lane < 27) {
+      const int q = nbr2[(int64_t)cell * 27 + lane];
+      if (q >= 0) { occ = mask64[q]; base = first0[q]; }
+    }
+    const uint32_t occ_lo = (uint32_t)occ, occ_hi = (uint32_t)(occ >> 32);
+    float fval[ROUNDS];
+    uint32_t pres[ROUNDS];
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      const int t = rd * 32 + lane;
+      const int tt = t < KV ? t : 0;
+      const int px = lx + (tt % KS) - R, py = ly + (tt / KS) % KS - R, pz = lz + tt / (KS * KS) - R;
+      const int j = ((px >> 2) + 1) + 3 * ((py >> 2) + 1) + 9 * ((pz >> 2) + 1);
+      const uint32_t bit = morton6(px & 3, py & 3, pz & 3);
+      const uint32_t lo = __shfl_sync(0xffffffffu, occ_lo, j), hi = __shfl_sync(0xffffffffu, occ_hi, j);
+      const int b0 = __shfl_sync(0xffffffffu, base, j);
+      const unsigned long long o = ((unsigned long long)hi << 32) | lo;
+      const bool p = t < KV && ((o >> bit) & 1ull);
+      fval[rd] = p ? f0[b0 + __popcll(o & ((1ull << bit) - 1ull))] : 0.f;
+      pres[rd] = __ballot_sync(0xffffffffu, p);
+    }
+    for (int c0 = 0; c0 < cout; c0 += 32) {
+      const int c = c0 + lane;
+      float acc = 0.f;
+#pragma unroll
+      for (int rd = 0; rd < ROUNDS; ++rd) {
+        uint32_t bal = pres[rd];
+        while (bal) {
+          const int src = __ffs(bal) - 1;
+          bal &= bal - 1;
+          const float f = __shfl_sync(0xffffffffu, fval[rd], src);
+          if (c < cout) acc = fmaf(f, s_w0[(rd * 32 + src) * cout + c], acc);
+        }
+      }
+      if (c < cout) {
+        float v = acc * (scale ? scale[c] : 1.f) + (shift ? shift[c] : 0.f);
+        if (relu) v = fmaxf(v, 0.f);
+        out[(size_t)r * cout + c] = v;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// row-wise / per-cloud operators
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_gather_rows1(const float *__restrict__ in, const int *__restrict__ perm, int n, float *__restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[perm[i]];
+}
+
+// per-cloud column reduction, deterministic two-stage: block (b, s) reduces slice s of cloud b's rows.
+// mode 0: sum x ; 1: sum clamp(x, eps)^p (GeM) ; 2: max x
+__global__ void k_pool_partial(const float *__restrict__ x, const int *__restrict__ boff, int c, int slices, int mode,
+                               float p, float eps, float *__restrict__ part /* (B, slices, c) */) {
+  const int b = blockIdx.x, s = blockIdx.y;
+  const int r0 = boff[b], r1 = boff[b + 1];
+  const int len = r1 - r0;
+  const int a0 = r0 + (int)(((int64_t)len * s) / slices), a1 = r0 + (int)(((int64_t)len * (s + 1)) / slices);
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float acc = mode == 2 ? -INFINITY : 0.f;
+    for (int r = a0; r < a1; ++r) {
+      const float v = x[(size_t)r * c + ch];
+      if (mode == 0) acc += v;
+      else if (mode == 1) acc += powf(fmaxf(v, eps), p);
+      else acc = fmaxf(acc, v);
+    }
+    part[((size_t)b * slices + s) * c + ch] = acc;
+  }
+}
+__global__ void k_pool_final(const float *__restrict__ part, const int *__restrict__ boff, int c, int slices, int mode, float p,
+                             float *__restrict__ out /* (B,c) */) {
+  const int b = blockIdx.x;
+  const int len = boff[b + 1] - boff[b];
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float acc = mode == 2 ? -INFINITY : 0.f;
+    for (int s = 0; s < slices; ++s) {
+      const float v = part[((size_t)b * slices + s) * c + ch];
+      acc = mode == 2 ? fmaxf(acc, v) : acc + v;
+    }
+    float r;
+    if (len == 0) r = 0.f;
+    else if (mode == 0) r = acc / (float)len;
+    else if (mode == 1) r = powf(acc / (float)len, 1.0f / p);
+    else r = acc;
+    out[(size_t)b * c + ch] = r;
+  }
+}
+// ECA gate (layers/eca_block.py:21-31): mean -> Conv1d(1,1,k, zero pad, no bias) over channels -> sigmoid
+__global__ void k_eca_gate(const float *__restrict__ part, const int *__restrict__ boff, int c, int slices,
+                           const float *__restrict__ wk, int k, float *__restrict__ gate /* (B,c) */) {
+  extern __shared__ float s_mean[];
+  const int b = blockIdx.x;
+  const int len = boff[b + 1] - boff[b];
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < slices; ++s) acc += part[((size_t)b * slices + s) * c + ch];
+    s_mean[ch] = len ? acc / (float)len : 0.f;
+  }
+  __syncthreads();
+  const int pad = (k - 1) / 2;
+  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+    float y = 0.f;
+    for (int j = 0; j < k; ++j) {
+      const int cc = ch + j - pad;
+      if (cc >= 0 && cc < c) y = fmaf(wk[j], s_mean[cc], y);
+    }
+    gate[(size_t)b * c + ch] = 1.f / (1.f + expf(-y));
+  }
+}
+// out = relu(t * gate[batch(row)] + res)   (layers/eca_block.py:36,70-71); gate == null -> plain BasicBlock
+__global__ void k_eca_apply(const float4 *__restrict__ t, const float4 *__restrict__ res, const float *__restrict__ gate,
+                            const uint64_t *__restrict__ keys, int batch_shift, int n, int c4, int relu, float4 *__restrict__ out) {
+  const int64_t total = (int64_t)n * c4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4), q = (int)(i % c4);
+    float4 v = t[i];
+    if (gate) {
+      const int b = (int)(keys[r] >> batch_shift);
+      const float4 g = *(const float4 *)(gate + ((size_t)b * c4 + q) * 4);
+      v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+    }
+    if (res) { const float4 rr = res[i]; v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    out[i] = v;
+  }
+}
+__global__ void k_bcast_mul(const float *__restrict__ x, const float *__restrict__ g, const uint64_t *__restrict__ keys,
+                            int batch_shift, int n, int c, float *__restrict__ out) {
+  const int64_t total = (int64_t)n * c;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c), ch = (int)(i % c);
+    out[i] = x[i] * g[(size_t)(keys[r] >> batch_shift) * c + ch];
+  }
+}
+// F.normalize(x, p=2, dim=1, eps=1e-12): one warp per row
+__global__ void k_l2norm_rows(const float *__restrict__ x, int n, int c, float *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+    float ss = 0.f;
+    for (int ch = lane; ch < c; ch += 32) { const float v = x[(size_t)r * c + ch]; ss = fmaf(v, v, ss); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    for (int ch = lane; ch < c; ch += 32) out[(size_t)r * c + ch] = x[(size_t)r * c + ch] * inv;
+  }
+}
+// keypoint offset tanh + Quantizer.keypoint_position (datasets/quantization.py:60-72, 93-103); sigma softplus
+__global__ void k_kp_sigma(const float *__restrict__ kp_raw /* (n,3) */, const float *__restrict__ sg_raw /* (n,1) */,
+                           const uint64_t *__restrict__ keys, int level, int n, int polar, float q0, float q1, float q2,
+                           int ignore_offset, float *__restrict__ kp_out, float *__restrict__ sg_out) {
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    if (kp_out) {
+      uint32_t b, vx, vy, vz;
+      split_key(level, keys[r], b, vx, vy, vz);
+      const float cx = (float)((int)(vx << level) - kAxisBias), cy = (float)((int)(vy << level) - kAxisBias),
+                  cz = (float)((int)(vz << level) - kAxisBias);
+      const float st = (float)(1 << level);
+      float ox = 0.f, oy = 0.f, oz = 0.f;
+      if (!ignore_offset) { ox = tanhf(kp_raw[3 * (size_t)r]); oy = tanhf(kp_raw[3 * (size_t)r + 1]); oz = tanhf(kp_raw[3 * (size_t)r + 2]); }
+      const float qy = polar ? q1 : q0, qz = polar ? q2 : q0;
+      // (c + 0.5) * q + off * (stride * q) / 2
+      const float kx = __fadd_rn(__fmul_rn(cx + 0.5f, q0), __fmul_rn(__fmul_rn(ox, __fmul_rn(st, q0)), 0.5f));
+      const float ky = __fadd_rn(__fmul_rn(cy + 0.5f, qy), __fmul_rn(__fmul_rn(oy, __fmul_rn(st, qy)), 0.5f));
+      const float kz = __fadd_rn(__fmul_rn(cz + 0.5f, qz), __fmul_rn(__fmul_rn(oz, __fmul_rn(st, qz)), 0.5f));
+      if (polar) {
+        const float th = __fdiv_rn(__fmul_rn(3.14159265358979323846f, kx - 180.f), 180.f);
+        kp_out[3 * (size_t)r] = cosf(th) * ky;
+        kp_out[3 * (size_t)r + 1] = sinf(th) * ky;
+        kp_out[3 * (size_t)r + 2] = kz;
+      } else {
+        kp_out[3 * (size_t)r] = kx; kp_out[3 * (size_t)r + 1] = ky; kp_out[3 * (size_t)r + 2] = kz;
+      }
+    }
+    if (sg_out) {
+      const float x = sg_raw[r];
+      sg_out[r] = x > 20.f ? x : log1pf(expf(x));
+    }
+  }
+}
+
+// per-cloud k smallest sigma (eval/evaluate.py:352-361): one CTA per cloud, k rounds of block arg-min over the
+// elements lexicographically greater than the previous pick (value, then row) - stable, no marking needed.
+__global__ void __launch_bounds__(256) k_topk_smallest(const float *__restrict__ sigma, const int *__restrict__ off, int k,
+                                                       int smem_cap, int *__restrict__ idx_out) {
+  extern __shared__ float s_val[];
+  __shared__ float s_bv[8];
+  __shared__ int s_bi[8];
+  __shared__ float s_pv;
+  __shared__ int s_pi;
+  const int b = blockIdx.x, r0 = off[b], len = off[b + 1] - r0;
+  const bool in_smem = len <= smem_cap;
+  if (in_smem)
+    for (int i = threadIdx.x; i < len; i += blockDim.x) s_val[i] = sigma[r0 + i];
+  if (threadIdx.x == 0) { s_pv = -INFINITY; s_pi = -1; }
+  __syncthreads();
+  for (int j = 0; j < k; ++j) {
+    const float pv = s_pv;
+    const int pi = s_pi;
+    float bv = INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+      const float v = in_smem ? s_val[i] : sigma[r0 + i];
+      const bool after = v > pv || (v == pv && i > pi);
+      if (after && (v < bv || (v == bv && i < bi))) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { s_bv[threadIdx.x >> 5] = bv; s_bi[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (s_bi[w] != 0x7fffffff && (bi == 0x7fffffff || s_bv[w] < bv || (s_bv[w] == bv && s_bi[w] < bi))) { bv = s_bv[w]; bi = s_bi[w]; }
+      const bool ok = bi != 0x7fffffff;
+      idx_out[(size_t)b * k + j] = ok ? bi : -1;
+      if (ok) { s_pv = bv; s_pi = bi; } else { s_pv = INFINITY; s_pi = 0x7fffffff; }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// host-side launchers
+// ------------------------------------------------------------------------------------------------------
+int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const float *scale, const float *shift, int cout,
+              int relu, float *out, cudaStream_t s) {
+  const Pyramid &py = ctx->pyr;
+  EGN_CHECK(ksize == 5 || ksize == 3, EGN_ERR_INVALID, "conv0: kernel size %d not supported (3 or 5)", ksize);
+  const int n0 = py.n[0];
+  const int threads = 256, blocks = grid_for((int64_t)n0 * 32, threads, 16);
+  const double pairs = (double)py.pairs_conv0;  // profile mode only (0 otherwise)
+  const double bytes = pairs * (1 + cout) * 4 + pairs * 8 + (double)ksize * ksize * ksize * cout * 4, flops = 2.0 * pairs * cout;
+  if (ksize == 5) {
+    const size_t smem = (size_t)125 * cout * 4;
+    EGN_CHECK(smem <= 200 * 1024, EGN_ERR_INVALID, "conv0: cout too large");
+    if (smem > 48 * 1024) EGN_CUDA(cudaFuncSetAttribute(k_conv0<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    EGN_LAUNCH(ctx, "conv0_5x5x5", bytes, flops, s,
+               k_conv0<5><<<blocks, threads, smem, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], py.mask64, py.first0, n0, w,
+                                                         scale, shift, cout, relu, out));
+  } else {
+    const size_t smem = (size_t)27 * cout * 4;
+    EGN_LAUNCH(ctx, "conv0_3x3x3", bytes, flops, s,
+               k_conv0<3><<<blocks, threads, smem, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], py.mask64, py.first0, n0, w,
+                                                         scale, shift, cout, relu, out));
+  }
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+
+// generic conv on the pyramid (cin >= 1); see egn_conv in the public header
+int run_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const float *w,
+             const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s) {
+  const Pyramid &py = ctx->pyr;
+  EGN_CHECK(py.valid, EGN_ERR_STATE, "conv before coords_build");
+  EGN_CHECK(cin >= 1 && cout >= 1 && in && w && out, EGN_ERR_INVALID, "conv: bad argument");
+  ConvArgs a = {};
+  a.in = in; a.out = out; a.w = w; a.scale = scale; a.shift = shift;
+  a.cin = cin; a.cout = cout; a.relu = relu; a.accumulate = accumulate;
+  long long pairs = 0;
+  if (ksize == 1) {
+    EGN_CHECK(level_in >= 0 && level_in < P, EGN_ERR_INVALID, "conv: bad level");
+    a.mode = G_IDENTITY; a.K = 1; a.n_out = py.n[level_in];
+    pairs = a.n_out;
+  } else if (ksize == 3) {
+    EGN_CHECK(level_in >= 1 && level_in < P, EGN_ERR_INVALID, "conv k=3: level must be 1..%d (level 0 has no neighbour table)", P - 1);
+    a.mode = G_NBR27; a.K = 27; a.n_out = py.n[level_in]; a.nbr = py.nbr[level_in];
+    pairs = py.pairs27[level_in];
+  } else if (ksize == 2 && !transposed) {
+    EGN_CHECK(level_in >= 0 && level_in + 1 < P, EGN_ERR_INVALID, "conv k=2 s=2: bad level");
+    a.mode = G_CHILD8; a.K = 8; a.n_out = py.n[level_in + 1];
+    a.cstart = py.cstart[level_in + 1]; a.cmask = py.cmask[level_in + 1];
+    pairs = py.n[level_in];
+  } else if (ksize == 2 && transposed) {
+    EGN_CHECK(level_in >= 1 && level_in < P, EGN_ERR_INVALID, "transposed conv: bad level");
+    a.mode = G_PARENT; a.K = 8; a.n_out = py.n[level_in - 1];
+    a.up = py.up[level_in - 1]; a.keys = py.keys[level_in - 1];
+    pairs = a.n_out;
+  } else if (ksize == 5) {
+    EGN_CHECK(level_in == 0 && cin == 1 && !accumulate, EGN_ERR_INVALID, "conv k=5 is supported at level 0 with cin=1 only");
+    return run_conv0(ctx, 5, in, w, scale, shift, cout, relu, out, s);
+  } else {
+    EGN_CHECK(false, EGN_ERR_INVALID, "conv: unsupported kernel size %d", ksize);
+  }
+  return launch_sconv(ctx, a, pairs, s);
+}
+
+int op_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const float *w,
+            const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  return run_conv(ctx, level_in, ksize, transposed, cin, cout, in, w, scale, shift, relu, accumulate, out, s);
+}
+
+static int pool_slices(int n_rows, int n_batches) {
+  int s = (int)div_up(n_rows, (int64_t)n_batches * 256);
+  return s < 1 ? 1 : (s > 64 ? 64 : s);
+}
+
+// per-cloud pooling; part must hold n_batches*slices*c floats (taken from the feature arena by the caller)
+int run_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, float p, float eps, float *part, int slices,
+             float *out, cudaStream_t s) {
+  const Pyramid &py = ctx->pyr;
+  const int B = py.n_batches;
+  const int threads = c >= 256 ? 256 : (c < 32 ? 32 : c);
+  EGN_LAUNCH(ctx, "global_pool", (double)py.n[level] * c * 4, 0, s,
+             k_pool_partial<<<dim3(B, slices), threads, 0, s>>>(in, py.boff[level], c, slices, mode, p, eps, part));
+  EGN_LAUNCH(ctx, "global_pool", (double)B * (slices + 1) * c * 4, 0, s,
+             k_pool_final<<<B, threads, 0, s>>>(part, py.boff[level], c, slices, mode, p, out));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+
+int op_global_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, float p, float eps, float *out, cudaStream_t s) {
+  EGN_CHECK(ctx && ctx->pyr.valid, EGN_ERR_STATE, "global_pool before coords_build");
+  EGN_CHECK(level >= 0 && level < P && c >= 1 && in && out, EGN_ERR_INVALID, "global_pool: bad argument");
+  const Pyramid &py = ctx->pyr;
+  const int slices = pool_slices(py.n[level], py.n_batches);
+  // the sort scratch is dead after coords_build; reuse on the same stream is stream-ordered
+  EGN_TRY(ctx->scratch.reserve((size_t)py.n_batches * slices * c * 4 + 4096, s));
+  float *part = (float *)ctx->scratch.take((size_t)py.n_batches * slices * c * 4);
+  EGN_CHECK(part != nullptr, EGN_ERR_STATE, "scratch arena exhausted");
+  return run_pool(ctx, level, c, in, mode, p, eps, part, slices, out, s);
+}
+
+int op_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const float *g, float *out, cudaStream_t s) {
+  EGN_CHECK(ctx && ctx->pyr.valid, EGN_ERR_STATE, "broadcast_mul before coords_build");
+  EGN_CHECK(level >= 0 && level < P && c >= 1 && in && g && out, EGN_ERR_INVALID, "broadcast_mul: bad argument");
+  const Pyramid &py = ctx->pyr;
+  const int n = py.n[level];
+  if (n == 0) return EGN_OK;
+  EGN_LAUNCH(ctx, "broadcast_mul", (double)n * c * 8, 0, s,
+             k_bcast_mul<<<grid_for((int64_t)n * c, 256), 256, 0, s>>>(in, g, py.keys[level], kMortonBits - 3 * level, n, c, out));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+
+int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out, cudaStream_t s) {
+  EGN_CHECK(sigma && offsets && idx_out && n_batches >= 1 && k >= 1, EGN_ERR_INVALID, "topk: bad argument");
+  // clouds up to 12k rows are staged in shared memory, larger ones are re-read from L2
+  const int cap = 12 * 1024;
+  k_topk_smallest<<<n_batches, 256, (size_t)cap * 4, s>>>(sigma, offsets, k, cap, idx_out);
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+
+// exported to forward.cu
+int run_gather_rows1(egn_ctx *ctx, const float *in, const int *perm, int n, float *out, cudaStream_t s) {
+  EGN_LAUNCH(ctx, "gather_input_features", (double)n * 12, 0, s, k_gather_rows1<<<grid_for(n, 256), 256, 0, s>>>(in, perm, n, out));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+int run_eca_gate(egn_ctx *ctx, int level, int c, const float *t, const float *wk, int k, float *part, int slices, float *gate,
+                 cudaStream_t s) {
+  const Pyramid &py = ctx->pyr;
+  const int threads = c >= 256 ? 256 : (c < 32 ? 32 : c);
+  EGN_LAUNCH(ctx, "eca_pool", (double)py.n[level] * c * 4, 0, s,
+             k_pool_partial<<<dim3(py.n_batches, slices), threads, 0, s>>>(t, py.boff[level], c, slices, 0, 1.f, 0.f, part));
+  EGN_LAUNCH(ctx, "eca_gate", (double)py.n_batches * (slices + 1) * c * 4, 0, s,
+             k_eca_gate<<<py.n_batches, threads, (size_t)c * 4, s>>>(part, py.boff[level], c, slices, wk, k, gate));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+int run_eca_apply(egn_ctx *ctx, int level, int c, const float *t, const float *res, const float *gate, int relu, float *out,
+                  cudaStream_t s) {
+  const Pyramid &py = ctx->pyr;
+  const int n = py.n[level];
+  EGN_CHECK((c & 3) == 0, EGN_ERR_INVALID, "block channels must be a multiple of 4");
+  if (n == 0) return EGN_OK;
+  EGN_LAUNCH(ctx, "eca_apply_residual_relu", (double)n * c * 12, 0, s,
+             k_eca_apply<<<grid_for((int64_t)n * (c / 4), 256), 256, 0, s>>>((const float4 *)t, (const float4 *)res, gate, py.keys[level],
+                                                                               kMortonBits - 3 * level, n, c / 4, relu, (float4 *)out));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+int run_l2norm(egn_ctx *ctx, const float *x, int n, int c, float *out, cudaStream_t s) {
+  if (n == 0) return EGN_OK;
+  EGN_LAUNCH(ctx, "l2_normalize_rows", (double)n * c * 8, 0, s, k_l2norm_rows<<<grid_for((int64_t)n * 32, 256), 256, 0, s>>>(x, n, c, out));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+int run_kp_sigma(egn_ctx *ctx, int level, const float *kp_raw, const float *sg_raw, int polar, const float q[3], int ignore_offset,
+                 float *kp_out, float *sg_out, cudaStream_t s) {
+  const Pyramid &py = ctx->pyr;
+  const int n = py.n[level];
+  if (n == 0) return EGN_OK;
+  EGN_LAUNCH(ctx, "keypoint_position_sigma", (double)n * 40, 0, s,
+             k_kp_sigma<<<grid_for(n, 128), 128, 0, s>>>(kp_raw, sg_raw, py.keys[level], level, n, polar, q[0], q[1], q[2], ignore_offset,
+                                                         kp_out, sg_out));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+int pool_slices_for(egn_ctx *ctx, int level) { return pool_slices(ctx->pyr.n[level], ctx->pyr.n_batches); }
+
+}  // namespace egn

@@ -1,0 +1,112 @@
+"""Pack a reference ``state_dict`` (key names of SURVEY.md Appendix B) into the single f32 device blob +
+``egn_net`` descriptor that ``egn_forward`` consumes.  Eval-mode BatchNorm is folded to scale/shift
+(MinkowskiBatchNorm == torch.nn.BatchNorm1d, eps from the module), ``nn.Linear`` weights are
+transposed to the (Cin, Cout) layout of the convolution kernels and their bias becomes the epilogue shift."""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+
+from . import lib as L
+
+
+class _Blob:
+    def __init__(self):
+        self.chunks: List[torch.Tensor] = []
+        self.n = 0
+
+    def add(self, t: torch.Tensor) -> int:
+        t = t.detach().to(torch.float32).cpu().contiguous().reshape(-1)
+        off = self.n
+        pad = (-t.numel()) % 4                      # keep every tensor 16-byte aligned for float4 loads
+        self.chunks.append(t)
+        if pad:
+            self.chunks.append(torch.zeros(pad))
+        self.n += t.numel() + pad
+        return off
+
+    def tensor(self) -> torch.Tensor:
+        return torch.cat(self.chunks) if self.chunks else torch.zeros(4)
+
+
+def _bn_fold(sd, prefix, eps=1e-5):
+    w, b = sd[prefix + ".weight"].float(), sd[prefix + ".bias"].float()
+    m, v = sd[prefix + ".running_mean"].float(), sd[prefix + ".running_var"].float()
+    scale = w / torch.sqrt(v + eps)
+    return scale, b - m * scale
+
+
+def _conv(blob, kernel, bn=None) -> L.Layer:
+    k = kernel if kernel.dim() == 3 else kernel.unsqueeze(0)
+    lay = L.Layer(cin=k.shape[1], cout=k.shape[2], w=blob.add(k), scale=-1, shift=-1)
+    if bn is not None:
+        lay.scale, lay.shift = blob.add(bn[0]), blob.add(bn[1])
+    return lay
+
+
+def _linear(blob, sd, prefix) -> L.Layer:
+    w = sd[prefix + ".linear.weight"]                     # (out, in)
+    lay = L.Layer(cin=w.shape[1], cout=w.shape[0], w=blob.add(w.t()), scale=-1, shift=-1)
+    if prefix + ".linear.bias" in sd:
+        lay.shift = blob.add(sd[prefix + ".linear.bias"])
+    return lay
+
+
+def _head(blob, sd, prefix, levels, out_channels) -> L.Head:
+    h = L.Head()
+    h.n_levels = len(levels)
+    for i, lv in enumerate(sorted(levels)):
+        h.levels[i] = lv
+    h.out_channels = out_channels
+    for lv in levels:
+        h.conv1x1[lv] = _conv(blob, sd[f"{prefix}.conv1x1.{lv}.kernel"])
+    for lv in range(min(levels) + 1, max(levels) + 1):
+        h.tconv[lv] = _conv(blob, sd[f"{prefix}.tconv.{lv}.kernel"])
+    return h
+
+
+def pack_egonn(sd: Dict[str, torch.Tensor], quantizer_desc: dict, global_levels=(5, 6, 7), local_levels=(3, 4),
+               ignore_keypoint_regressor: bool = False, bn_eps: float = 1e-5):
+    """state_dict of models/minkgl.py:MinkGL (built by models/model_factory.py:31-78) -> (blob cpu f32, Net)."""
+    blob = _Blob()
+    net = L.Net()
+    n_levels = 0
+    while f"trunk.convs.{n_levels + 1}.kernel" in sd:
+        n_levels += 1
+    net.n_levels = n_levels
+    k0 = sd["trunk.convs.0.kernel"]
+    net.conv0_ksize = int(round(k0.shape[0] ** (1.0 / 3.0)))
+    net.conv0 = _conv(blob, k0, _bn_fold(sd, "trunk.bn.0.bn", bn_eps))
+    for lv in range(1, n_levels + 1):
+        net.down[lv] = _conv(blob, sd[f"trunk.convs.{lv}.kernel"], _bn_fold(sd, f"trunk.bn.{lv}.bn", bn_eps))
+        p = f"trunk.blocks.{lv}.0"
+        assert f"trunk.blocks.{lv}.1.conv1.kernel" not in sd, "more than one block per level is not supported yet"
+        net.conv1[lv] = _conv(blob, sd[p + ".conv1.kernel"], _bn_fold(sd, p + ".norm1.bn", bn_eps))
+        net.conv2[lv] = _conv(blob, sd[p + ".conv2.kernel"], _bn_fold(sd, p + ".norm2.bn", bn_eps))
+        if p + ".downsample.0.kernel" in sd:
+            net.res[lv] = _conv(blob, sd[p + ".downsample.0.kernel"], _bn_fold(sd, p + ".downsample.1.bn", bn_eps))
+        if p + ".eca.conv.weight" in sd:
+            w = sd[p + ".eca.conv.weight"].reshape(-1)
+            net.eca_k[lv], net.eca_w[lv] = w.numel(), blob.add(w)
+    gc = sd[f"global_head.conv1x1.{max(global_levels)}.kernel"].shape[-1]
+    net.global_head = _head(blob, sd, "global_head", list(global_levels), gc)
+    net.global_mlp[0] = _linear(blob, sd, "global_descriptor_decoder.net.0")
+    net.global_mlp[1] = _linear(blob, sd, "global_descriptor_decoder.net.2")
+    net.pool_method = 0
+    net.gem_p = float(sd["global_pooling.pooling.p"].reshape(-1)[0])
+    net.gem_eps = 1e-6
+    if local_levels and f"local_head.conv1x1.{max(local_levels)}.kernel" in sd:
+        lc = sd[f"local_head.conv1x1.{max(local_levels)}.kernel"].shape[-1]
+        net.local_head = _head(blob, sd, "local_head", list(local_levels), lc)
+        for name, dst in (("local_descriptor_decoder", net.desc_mlp), ("local_keypoint_regressor", net.kp_mlp),
+                          ("local_sigma_regressor", net.sigma_mlp)):
+            dst[0] = _linear(blob, sd, name + ".net.0")
+            dst[1] = _linear(blob, sd, name + ".net.2")
+    net.polar = 1 if quantizer_desc["coordinates"] == "polar" else 0
+    step = quantizer_desc["step"]
+    step = list(step) if isinstance(step, (list, tuple)) else [step, step, step]
+    for i in range(3):
+        net.quant_step[i] = float(step[i])
+    net.ignore_keypoint_regressor = int(ignore_keypoint_regressor)
+    return blob.tensor(), net

@@ -1,0 +1,196 @@
+/*
+ * egonn_b200 - C ABI of the B200-native sparse-voxel descriptor-extraction engine.
+ *
+ * The reference (jac99/Egonn, /root/reference) has no FFI of its own: its forward path calls the
+ * third-party MinkowskiEngine Python API.  Each entry point below names the reference call site
+ * (file:line under /root/reference) whose work it replaces; MinkowskiEngine's own analogue would be
+ * its pybind module MinkowskiEngineBackend._C (quantize_th, CoordinateMapManagerGPU_c10,
+ * ConvolutionForwardGPU, ConvolutionTransposeForwardGPU, GlobalPoolingForwardGPU, BroadcastForwardGPU).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch types.  All data pointers are DEVICE pointers unless
+ *     the parameter is documented "host".  The caller owns every buffer it passes; the engine never frees
+ *     caller memory.  Engine-owned scratch lives in the egn_ctx and is borrowed until the next call.
+ *   - every function returns 0 on success or a negative egn_status; egn_last_error() gives the text.
+ *   - work is enqueued on the cudaStream_t passed as `stream` (void* to keep this header CUDA-free).
+ *     egn_coords_build / egn_quantize synchronise that stream once, because row counts must reach the host.
+ *   - one egn_ctx per (device, stream); contexts are independent (no global mutable state besides the
+ *     thread-local error string).
+ *   - coordinates are int32 [batch, x, y, z]; spatial range [-2^17, 2^17), batch index < 1023.
+ *   - rows of every coordinate map are kept in the engine's canonical order: ascending
+ *     (batch, Morton(z,y,x)) - MinkowskiEngine's row order is not a contract.
+ *   - there is NO CPU fallback: every entry point needs a CUDA device.
+ */
+#ifndef EGONN_B200_H
+#define EGONN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EGN_MAX_LEVELS 8   /* network levels 0..7 (tensor stride 1..128) */
+#define EGN_PYR_LEVELS 10  /* coordinate pyramid levels kept per context: 0..9 */
+#define EGN_MAX_HEAD_LEVELS 4
+
+typedef struct egn_ctx egn_ctx;
+typedef void *egn_stream_t; /* cudaStream_t */
+
+typedef enum {
+  EGN_OK = 0,
+  EGN_ERR_INVALID = -1,  /* bad argument */
+  EGN_ERR_CUDA = -2,     /* CUDA runtime error (text in egn_last_error) */
+  EGN_ERR_RANGE = -3,    /* coordinate / batch index outside the supported range */
+  EGN_ERR_STATE = -4,    /* call order (e.g. forward before coords_build) */
+  EGN_ERR_CAPACITY = -5  /* an output buffer is too small */
+} egn_status;
+
+const char *egn_last_error(void);
+int egn_version(void);
+
+/* ---- context = coordinate manager + scratch arena ------------------------------------------------
+ * Replaces: the MinkowskiEngine CoordinateManager created by ME.SparseTensor(features, coordinates=...)
+ * at models/minkgl.py:269 (and again by layers/pooling.py:84). */
+int egn_ctx_create(egn_ctx **out, int device);
+int egn_ctx_destroy(egn_ctx *ctx);
+
+/* ---- voxel quantisation ---------------------------------------------------------------------------
+ * Replaces: CartesianQuantizer.__call__ datasets/quantization.py:79-85 and PolarQuantizer.__call__
+ * :29-44, i.e. ME.utils.sparse_quantize(pc, quantization_size=q, return_index=True):
+ * floor(f32 divide), int32, first-occurrence-wins de-duplication, survivors in input order.
+ *   points      (n,3) f32        coords_out (n,3) int32 [capacity n]     index_out (n) int64 [capacity n]
+ *   polar != 0: (x,y,z) -> (180 + atan2(y,x)*180/pi, sqrt(x^2+y^2), z) / step[0..2] first (step = deg, m, m);
+ *   polar == 0: all three axes divided by step[0].
+ *   n_out (host) receives the number of voxels.  Synchronises `stream`. */
+int egn_quantize(egn_ctx *ctx, const float *points, int64_t n, const float step[3], int polar,
+                 int32_t *coords_out, int64_t *index_out, int64_t *n_out, egn_stream_t stream);
+
+/* ---- coordinate pyramid + kernel maps ---------------------------------------------------------------
+ * Replaces: the coordinate hash-table build of ME.SparseTensor (models/minkgl.py:269), the strided maps
+ * created by the kernel-2 stride-2 convolutions (models/minkgl.py:104-105,145-146) and the 3x3x3 / 5x5x5 /
+ * 2x2x2 kernel maps MinkowskiEngine generates and caches for models/minkgl.py:140-151 and
+ * layers/eca_block.py:59-64. */
+typedef struct {
+  int32_t n_batches;                 /* max batch index + 1 */
+  int32_t n_input;                   /* rows passed in */
+  int32_t n_rows[EGN_PYR_LEVELS];    /* rows of the level-L map (n_rows[0] < n_input if duplicates were dropped) */
+  int32_t status;                    /* egn_status of the device-side validation */
+} egn_coords_info;
+
+/* coords (n,4) int32 [b,x,y,z], any order; duplicates keep the first occurrence (ME RANDOM_SUBSAMPLE
+ * keeps one arbitrary row).  Builds levels 0..9, child/parent links and the 27-neighbour tables.
+ * info (host) is filled; synchronises `stream` once. */
+int egn_coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n, egn_coords_info *info, egn_stream_t stream);
+
+/* Copy the coordinates of level L (tensor stride 2^L) into out (n_rows[L],4) int32, canonical order. */
+int egn_coords_get(egn_ctx *ctx, int level, int32_t *out, egn_stream_t stream);
+/* Input row that became canonical L0 row r: out (n_rows[0]) int32. */
+int egn_coords_input_rows(egn_ctx *ctx, int32_t *out, egn_stream_t stream);
+/* First row of each batch index at level L: out (n_batches+1) int32. */
+int egn_coords_batch_offsets(egn_ctx *ctx, int level, int32_t *out, egn_stream_t stream);
+/* 27-neighbour table of level L >= 1 (k = kx + 3(ky + 3kz)): out (n_rows[L],27) int32, -1 = absent. */
+int egn_coords_neighbors(egn_ctx *ctx, int level, int32_t *out, egn_stream_t stream);
+
+/* ---- network description (weights live in one caller-owned f32 device blob; fields are offsets in floats,
+ *      -1 = absent).  Filled by egonn_b200/weights.py from the reference state_dict. */
+typedef struct {
+  int32_t cin, cout;
+  int64_t w;      /* (K,cin,cout) kernel, K = 125/27/8/1 */
+  int64_t scale;  /* (cout) folded eval-mode BatchNorm scale gamma/sqrt(var+eps), or -1 */
+  int64_t shift;  /* (cout) folded BatchNorm shift / Linear bias, or -1 */
+} egn_layer;
+
+typedef struct {
+  int32_t n_levels;                       /* number of input levels, 0 = head absent */
+  int32_t levels[EGN_MAX_HEAD_LEVELS];    /* ascending trunk levels feeding the head */
+  int32_t out_channels;
+  egn_layer conv1x1[EGN_MAX_LEVELS];      /* indexed by trunk level */
+  egn_layer tconv[EGN_MAX_LEVELS];        /* tconv[L]: level L -> L-1 */
+} egn_head;
+
+typedef struct {
+  int32_t n_levels;                       /* trunk levels 1..n_levels */
+  int32_t conv0_ksize;                    /* 5 (or 3) */
+  egn_layer conv0;                        /* + BN + ReLU    models/minkgl.py:100-102,140-142 */
+  egn_layer down[EGN_MAX_LEVELS];         /* [L] 2x2x2 stride-2 + BN + ReLU   :104-107,145-148 */
+  egn_layer conv1[EGN_MAX_LEVELS];        /* [L] block conv1 + norm1 + ReLU   layers/eca_block.py:59-61 */
+  egn_layer conv2[EGN_MAX_LEVELS];        /* [L] block conv2 + norm2          :63-64 */
+  egn_layer res[EGN_MAX_LEVELS];          /* [L] downsample 1x1 + BN (cin == 0: identity)  models/minkgl.py:121-126 */
+  int32_t eca_k[EGN_MAX_LEVELS];          /* ECA Conv1d kernel size (0 = plain BasicBlock)  layers/eca_block.py:14-17 */
+  int64_t eca_w[EGN_MAX_LEVELS];
+  egn_head global_head;                   /* models/minkgl.py:46-60 */
+  egn_head local_head;
+  egn_layer global_mlp[2];                /* DescriptorDecoder (cin == 0: absent)  models/minkgl.py:207-225 */
+  int32_t pool_method;                    /* 0 GeM, 1 SPoC (mean), 2 MAC (max)     layers/pooling.py:46-86 */
+  float gem_p, gem_eps;
+  egn_layer desc_mlp[2];                  /* local DescriptorDecoder + L2 normalise */
+  egn_layer kp_mlp[2];                    /* KeypointRegressor + tanh      models/minkgl.py:175-185 */
+  egn_layer sigma_mlp[2];                 /* SigmaRegressor + softplus     models/minkgl.py:188-204 */
+  int32_t polar;                          /* keypoint_position: datasets/quantization.py:60-72 / :93-103 */
+  float quant_step[3];
+  int32_t ignore_keypoint_regressor;      /* models/minkgl.py:296-299 */
+} egn_net;
+
+/* ---- whole forward ----------------------------------------------------------------------------------
+ * Replaces: MinkGL.forward models/minkgl.py:267-315 (MinkTrunk.forward :136-153, MinkHead.forward :46-60,
+ * ECABasicBlock.forward layers/eca_block.py:56-73, GeM.forward layers/pooling.py:82-86, the three
+ * regressors/decoders and Quantizer.keypoint_position) and MinkLoc.forward models/minkloc.py:44-61.
+ * Requires egn_coords_build on the same ctx.  features (n_input) f32 in INPUT row order.
+ *   global_out       (n_batches, global dim) f32, or NULL to skip the global head
+ *   desc_out         (n_rows[Llocal], desc dim) f32 |
+ *   keypoints_out    (n_rows[Llocal], 3) f32        |  all NULL to skip the local head
+ *   sigma_out        (n_rows[Llocal], 1) f32        |
+ * Local rows are in canonical order of level Llocal = min(local_head.levels); use egn_coords_get /
+ * egn_coords_batch_offsets to split them per cloud.  Asynchronous on `stream`. */
+int egn_forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float *features,
+                float *global_out, float *desc_out, float *keypoints_out, float *sigma_out,
+                egn_stream_t stream);
+
+/* Debug / parity taps: copy an intermediate feature map of the last egn_forward.
+ * which: 0 conv0 output (L0), 1 down-conv output of `level`, 2 block output of `level`,
+ *        3 global head map, 4 local head map.  out must hold rows*channels floats. */
+int egn_forward_tap(egn_ctx *ctx, int which, int level, float *out, egn_stream_t stream);
+
+/* ---- single operators on the context's coordinate maps (the MinkowskiEngine-shaped shim calls these) ----
+ * Replaces: ME.MinkowskiConvolution / MinkowskiConvolutionTranspose forward.
+ * ksize 1|3 (stride 1), 2 (stride 2: level_in -> level_in+1), 5 (level 0 only, cin == 1);
+ * transposed != 0 with ksize 2: level_in -> level_in-1 on the existing map.
+ * out = act((conv) * scale + shift) [+ out if accumulate]; scale/shift may be NULL; relu 0|1. */
+int egn_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout,
+             const float *in, const float *w, const float *scale, const float *shift, int relu,
+             int accumulate, float *out, egn_stream_t stream);
+/* Replaces: ME.MinkowskiGlobalPooling / GlobalAvgPooling / GlobalMaxPooling: out (n_batches, c). */
+int egn_global_pool(egn_ctx *ctx, int level, int c, const float *in, int is_max, float *out, egn_stream_t stream);
+/* Replaces: ME.MinkowskiBroadcastMultiplication: out[r] = in[r] * g[batch(r)]. */
+int egn_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const float *g, float *out, egn_stream_t stream);
+
+/* ---- "next" rows: keypoint selection on device -------------------------------------------
+ * Replaces: get_keypoints_idxes eval/evaluate.py:352-361 (torch.topk(sigma, k, largest=False)) per cloud.
+ * sigma (n) f32, offsets (n_batches+1) int32 device; idx_out (n_batches,k) int32 rows (cloud-relative),
+ * ascending sigma, ties by lower row; -1 padding when a cloud has fewer than k rows. */
+int egn_topk_smallest(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out,
+                      egn_stream_t stream);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------------------
+ * egn_profile_enable(ctx, 1): every kernel class launched by this context is bracketed by CUDA events on its
+ * stream and the pair counts needed for the algorithmic-byte model are computed at coords_build.
+ * egn_profile_read drains the finished events into per-class totals (synchronises the events, not the device).
+ * alg_bytes follows SURVEY.md 8(d): conv P*(Cin+Cout)*4 + P*8 + K*Cin*Cout*4; row-wise R*(Cin+Cout)*4;
+ * kernel-map build N*8 + N*K*4.  egn_launch_count: kernels of THIS library launched so far by the context. */
+typedef struct {
+  char name[48];
+  int64_t launches;
+  double ms;         /* summed device time between the class's start/stop events */
+  double alg_bytes;  /* summed algorithmic bytes */
+  double flops;      /* summed useful FLOPs (2*P*Cin*Cout for convolutions) */
+} egn_profile_entry;
+int egn_profile_enable(egn_ctx *ctx, int enable);
+int egn_profile_read(egn_ctx *ctx, egn_profile_entry *out, int capacity, int *n_out, int reset);
+int64_t egn_launch_count(egn_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EGONN_B200_H */

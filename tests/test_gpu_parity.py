@@ -1,0 +1,233 @@
+"""-m gpu parity tests proper: the CUDA engine through the C ABI against the CPU oracle on the same
+seeded inputs and against the committed golden vectors (produced by the unmodified reference graph code).
+
+Bars (north_star): coordinates / indices bit-exact (compared keyed by coordinate - ME row order is not a
+contract); floating-point tensors within 1e-3 relative (max|a-b| / max|b| per tensor)."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+from gpu_common import RTOL, assert_close_rel, lex_order
+from oracle import egonn_oracle, me_ops
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    return torch.device("cuda", 0)
+
+
+def _model(weights, quant, cuda):
+    import egonn_b200 as E
+    mp = E.ModelParams.from_dict(model="egonn", coordinates=quant["coordinates"], quantization_step=quant["step"])
+    m = E.model_factory(mp)
+    m.load_state_dict(weights)
+    return m.eval().to(cuda), mp
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", list(GOLDEN_CASES))
+def test_quantize_bit_exact_vs_golden(case, cuda):
+    import egonn_b200 as E
+    g = load_golden(case)
+    quant = GOLDEN_CASES[case]
+    q = (E.PolarQuantizer(quant["step"]) if quant["coordinates"] == "polar" else E.CartesianQuantizer(quant["step"]))
+    sp = g["points_splits"]
+    coords, index = [], []
+    for i in range(int(g["n_clouds"])):
+        c, ndx = q(torch.from_numpy(g["points"][sp[i]:sp[i + 1]]).to(cuda))
+        assert c.dtype == torch.int32 and ndx.dtype == torch.int64 and c.is_cuda
+        coords.append(c)
+        index.append(ndx.cpu().numpy())
+    bc = E.batched_coordinates(coords).cpu().numpy()
+    if quant["coordinates"] == "cartesian":
+        assert np.array_equal(bc, g["coords"])
+        assert np.array_equal(np.concatenate(index), g["quant_index"])
+    else:
+        # polar: atan2f on the GPU and SLEEF atan2 on the CPU may differ by an ulp -> a point exactly on a
+        # sector boundary can land in the neighbouring voxel.  Policy: identical voxel SET up to 1e-3 of voxels.
+        a = set(map(tuple, bc.tolist()))
+        b = set(map(tuple, g["coords"].tolist()))
+        assert len(a ^ b) <= 1e-3 * len(b), f"{len(a ^ b)} differing voxels of {len(b)}"
+
+
+@pytest.mark.parametrize("case", list(GOLDEN_CASES))
+def test_pyramid_levels_bit_exact(case, cuda):
+    """All strided coordinate maps == unique(floor(c / 2^L) * 2^L) of the golden vectors, bit-exact."""
+    import egonn_b200 as E
+    g = load_golden(case)
+    eng = E.Engine(cuda)
+    info = eng.build(torch.from_numpy(g["coords"]).to(cuda))
+    assert info.n_batches == int(g["n_clouds"]) and info.n_rows[0] == g["coords"].shape[0]
+    c0 = eng.level_coords(0).cpu().numpy()
+    assert np.array_equal(c0[lex_order(eng.level_coords(0))], g["coords"][me_ops.canonical_order(g["coords"])])
+    rows = eng.input_rows().cpu().numpy()
+    assert np.array_equal(g["coords"][rows], c0)                       # canonical row r came from input row rows[r]
+    for L in range(1, 8):
+        cl = eng.level_coords(L)
+        assert np.array_equal(cl.cpu().numpy()[lex_order(cl)], g[f"coords_L{L}"]), f"level {L}"
+        off = eng.batch_offsets(L).cpu().numpy()
+        b = cl.cpu().numpy()[:, 0]
+        assert off[0] == 0 and off[-1] == cl.shape[0]
+        for i in range(info.n_batches):
+            assert np.all(b[off[i]:off[i + 1]] == i)
+
+
+def test_neighbor_tables_vs_oracle_kernel_map(cuda):
+    """27-neighbour tables (k = kx + 3ky + 9kz) == the oracle's kernel map, pair for pair."""
+    import egonn_b200 as E
+    g = load_golden("mini3_cartesian")
+    eng = E.Engine(cuda)
+    eng.build(torch.from_numpy(g["coords"]).to(cuda))
+    cm = me_ops.CoordinateManager(g["coords"])
+    s = 1
+    for L in range(1, 8):
+        s = cm.stride_map(s)
+        cl = eng.level_coords(L).cpu().numpy()
+        nbr = eng.neighbors(L).cpu().numpy()
+        oc = cm.coords(s)
+        # map oracle rows -> engine rows through the coordinates
+        o2e = np.empty(oc.shape[0], dtype=np.int64)
+        o2e[me_ops.canonical_order(oc)] = me_ops.canonical_order(cl)
+        pairs = cm.kernel_map(s, s, 3)
+        expect = np.full_like(nbr, -1)
+        for k, (i_rows, o_rows) in enumerate(pairs):
+            expect[o2e[o_rows], k] = o2e[i_rows]
+        assert np.array_equal(nbr, expect), f"level {L}"
+
+
+def test_duplicates_and_errors(cuda):
+    import egonn_b200 as E
+    from egonn_b200.lib import EgnError
+    eng = E.Engine(cuda)
+    c = torch.tensor([[0, 1, 2, 3], [0, 1, 2, 3], [0, -5, 0, 9], [1, 1, 2, 3]], dtype=torch.int32, device=cuda)
+    info = eng.build(c)
+    assert info.n_rows[0] == 3 and info.n_batches == 2
+    assert eng.input_rows().cpu().tolist().count(1) == 0             # first occurrence (row 0) wins
+    with pytest.raises(EgnError):
+        eng.build(torch.tensor([[0, 1 << 17, 0, 0]], dtype=torch.int32, device=cuda))
+    with pytest.raises(EgnError):
+        eng.build(torch.tensor([[1023, 0, 0, 0]], dtype=torch.int32, device=cuda))
+    with pytest.raises(EgnError):
+        eng.build(torch.zeros((1, 4), dtype=torch.int32))           # CPU tensor: no CPU path
+    # extreme but legal coordinates
+    c = torch.tensor([[0, -(1 << 17), (1 << 17) - 1, 0], [1022, (1 << 17) - 1, -(1 << 17), -1]], dtype=torch.int32, device=cuda)
+    info = eng.build(c)
+    assert info.n_rows[0] == 2
+    got = eng.level_coords(0).cpu().numpy()
+    assert set(map(tuple, got.tolist())) == set(map(tuple, c.cpu().numpy().tolist()))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", list(GOLDEN_CASES))
+def test_forward_vs_golden(case, cuda, weights):
+    """End-to-end forward == the unmodified reference graph code on the ME-semantics shim (golden vectors)."""
+    g = load_golden(case)
+    quant = GOLDEN_CASES[case]
+    model, _ = _model(weights, quant, cuda)
+    coords = torch.from_numpy(g["coords"]).to(cuda)
+    feats = torch.ones((coords.shape[0], 1), device=cuda)
+    p = model.forward_packed({"coords": coords, "features": feats})
+    torch.cuda.synchronize()
+    lc = p["local_coords"]
+    o = lex_order(lc)
+    assert np.array_equal(lc.cpu().numpy()[o], g["coords_L3"])      # keypoint identity = its L3 voxel: bit-exact
+    assert_close_rel(p["global"], torch.from_numpy(g["global"]), RTOL, "global")
+    assert_close_rel(p["descriptors"][o], torch.from_numpy(g["descriptors"]), RTOL, "descriptors")
+    assert_close_rel(p["keypoints"][o], torch.from_numpy(g["keypoints"]), RTOL, "keypoints")
+    assert_close_rel(p["sigma"][o], torch.from_numpy(g["sigma"]), RTOL, "sigma")
+    # intermediate taps
+    eng = model._engine
+    for L in (1, 3, 5, 7):
+        f = eng.tap(2, L, g[f"block{L}"].shape[1])
+        oo = lex_order(eng.level_coords(L))
+        assert_close_rel(f[oo], torch.from_numpy(g[f"block{L}"]), RTOL, f"block{L}")
+    # list API identical to the reference's return structure
+    y = model({"coords": coords, "features": feats})
+    assert set(y) == {"global", "descriptors", "keypoints", "sigma"}
+    nb = int(g["n_clouds"])
+    assert len(y["descriptors"]) == len(y["keypoints"]) == len(y["sigma"]) == nb
+    assert y["global"].shape == (nb, 256) and y["descriptors"][0].shape[1] == 128 and y["sigma"][0].shape[1] == 1
+
+
+def test_forward_vs_oracle_random_features_and_order(cuda, weights):
+    """Non-trivial input features, shuffled input rows, negative coordinates: engine vs oracle run here."""
+    g = load_golden("mini3_cartesian")
+    quant = GOLDEN_CASES["mini3_cartesian"]
+    rng = np.random.default_rng(5)
+    coords = g["coords"].copy()
+    coords[:, 1:] -= np.array([300, 17, 5], dtype=np.int32)
+    perm = rng.permutation(coords.shape[0])
+    coords = coords[perm]
+    feats = torch.from_numpy(rng.uniform(0.2, 1.8, (coords.shape[0], 1)).astype(np.float32))
+    ref = egonn_oracle.forward(weights, coords, feats, quant, keep_intermediates=True)
+    model, _ = _model(weights, quant, cuda)
+    p = model.forward_packed({"coords": torch.from_numpy(coords).to(cuda), "features": feats.to(cuda)})
+    o = lex_order(p["local_coords"])
+    assert np.array_equal(p["local_coords"].cpu().numpy()[o], ref["coords_L3"])
+    eng = model._engine
+    f0 = eng.tap(0, 0, 32)
+    assert_close_rel(f0[lex_order(eng.level_coords(0))], ref["features"]["conv0"], RTOL, "conv0")
+    for L in range(1, 8):
+        oo = lex_order(eng.level_coords(L))
+        assert_close_rel(eng.tap(1, L, ref["features"][f"down{L}"].shape[1])[oo], ref["features"][f"down{L}"], RTOL, f"down{L}")
+        assert_close_rel(eng.tap(2, L, ref["features"][f"block{L}"].shape[1])[oo], ref["features"][f"block{L}"], RTOL, f"block{L}")
+    assert_close_rel(p["global"], ref["global"], RTOL, "global")
+    assert_close_rel(p["descriptors"][o], ref["descriptors"], RTOL, "descriptors")
+    assert_close_rel(p["keypoints"][o], ref["keypoints"], RTOL, "keypoints")
+    assert_close_rel(p["sigma"][o], ref["sigma"], RTOL, "sigma")
+
+
+def test_layerwise_operator_path_matches_fused(cuda, weights):
+    """The MinkowskiEngine-shaped operator front end (one C-ABI call per op) == the fused egn_forward."""
+    g = load_golden("mini3_cartesian")
+    model, _ = _model(weights, GOLDEN_CASES["mini3_cartesian"], cuda)
+    batch = {"coords": torch.from_numpy(g["coords"]).to(cuda), "features": torch.ones((g["coords"].shape[0], 1), device=cuda)}
+    a = model(batch)
+    b = model.forward_layerwise(batch)
+    assert_close_rel(b["global"], a["global"], 1e-4, "global")
+    for k in ("descriptors", "keypoints", "sigma"):
+        for x, y in zip(a[k], b[k]):
+            assert_close_rel(y, x, 1e-4, k)
+
+
+def test_batch_independence_and_heads_switches(cuda, weights):
+    g = load_golden("mini3_cartesian")
+    quant = GOLDEN_CASES["mini3_cartesian"]
+    model, _ = _model(weights, quant, cuda)
+    coords = torch.from_numpy(g["coords"]).to(cuda)
+    feats = torch.ones((coords.shape[0], 1), device=cuda)
+    full = model({"coords": coords, "features": feats})
+    sel = coords[:, 0] == 1
+    one = coords[sel].clone()
+    one[:, 0] = 0
+    single = model({"coords": one, "features": feats[sel]})
+    assert_close_rel(single["global"][0], full["global"][1], 1e-5, "global of cloud 1 alone")
+    assert_close_rel(single["descriptors"][0], full["descriptors"][1], 1e-5, "descriptors of cloud 1 alone")
+    y = model({"coords": coords, "features": feats}, disable_local_head=True)
+    assert set(y) == {"global"}
+    y = model({"coords": coords, "features": feats}, disable_global_head=True)
+    assert set(y) == {"descriptors", "keypoints", "sigma"}
+    model.ignore_keypoint_regressor = True
+    z = model({"coords": coords, "features": feats})
+    centres = (model.last["local_coords"][0][:, 1:].float() + 0.5) * quant["step"]
+    assert_close_rel(z["keypoints"][0], centres, 1e-6, "keypoints at supervoxel centres")
+
+
+def test_topk_smallest_matches_torch(cuda):
+    import egonn_b200 as E
+    torch.manual_seed(0)
+    lens = [300, 5, 0, 1000]
+    off = torch.tensor(np.cumsum([0] + lens), dtype=torch.int32, device=cuda)
+    s = torch.rand(sum(lens), device=cuda)
+    s[10] = s[20]                                                   # a tie: lower row first
+    idx = E.topk_smallest(s, off, 128).cpu()
+    for b, n in enumerate(lens):
+        k = min(n, 128)
+        seg = s[off[b]:off[b + 1]].cpu()
+        exp = torch.sort(seg, stable=True).indices[:k]
+        assert torch.equal(idx[b, :k].long(), exp)
+        assert torch.all(idx[b, k:] == -1)
