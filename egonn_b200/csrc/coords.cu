@@ -309,20 +309,26 @@ __global__ void k_count_pairs_conv0(const uint64_t *__restrict__ keys0, const in
 }
 
 // ------------------------------------------------------------------------------------------------------
+static size_t sort_temp_bytes(int n, int end_bit) {
+  size_t temp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
+                                  (uint32_t *)nullptr, n, 0, end_bit, (cudaStream_t)0);
+  return temp_bytes;
+}
+
 static int sort_pairs(Arena &scratch, uint64_t *kin, uint64_t *kout, uint32_t *vin, uint32_t *vout, int n, int end_bit,
                       cudaStream_t s) {
-  size_t temp_bytes = 0;
-  EGN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, kin, kout, vin, vout, n, 0, end_bit, s));
+  size_t temp_bytes = sort_temp_bytes(n, end_bit);
   void *temp = scratch.take(temp_bytes);
-  EGN_CHECK(temp != nullptr, EGN_ERR_STATE, "scratch arena exhausted in sort_pairs");
+  EGN_CHECK(temp != nullptr, EGN_ERR_STATE, "scratch arena exhausted in sort_pairs (%zu bytes)", temp_bytes);
   EGN_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, n, 0, end_bit, s));
   return EGN_OK;
 }
 
 static size_t sort_scratch_bytes(int64_t n) {
-  // keys in/out, vals in/out, cub temp (onesweep: histograms + a few KB; bound generously), tile counts
+  // keys in/out, vals in/out, cub temp, tile counts, profile counters
   const int64_t nblocks = div_up(n, kTile);
-  return pad256(n * 8) * 2 + pad256(n * 4) * 2 + pad256(n * 1 + (1 << 20)) + pad256(nblocks * P * 4) + (1 << 16);
+  return pad256(n * 8) * 2 + pad256(n * 4) * 2 + pad256(sort_temp_bytes((int)n, 64)) + pad256(nblocks * P * 4) + (1 << 16);
 }
 
 int coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n64, egn_coords_info *info, cudaStream_t s) {

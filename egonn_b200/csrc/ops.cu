@@ -536,8 +536,8 @@ int op_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const floa
 
 int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out, cudaStream_t s) {
   EGN_CHECK(sigma && offsets && idx_out && n_batches >= 1 && k >= 1, EGN_ERR_INVALID, "topk: bad argument");
-  // clouds up to 12k rows are staged in shared memory, larger ones are re-read from L2
-  const int cap = 12 * 1024;
+  // clouds up to 8k rows are staged in shared memory, larger ones are re-read from L2
+  const int cap = 8 * 1024;
   k_topk_smallest<<<n_batches, 256, (size_t)cap * 4, s>>>(sigma, offsets, k, cap, idx_out);
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
