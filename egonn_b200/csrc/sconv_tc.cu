@@ -1,0 +1,375 @@
+// Tensor-core sparse convolution for sm_100a: output-stationary implicit GEMM with a GATHERED A operand.
+//
+//   out[o, :] = epilogue( sum_k  in[nbr(o,k), :] @ W[k] )          (MinkowskiConvolution forward)
+//
+// One CTA owns 128 consecutive output rows (UMMA M = 128, cta_group::1).  The reduction dimension
+// (kernel offset k) x (input channel) is cut into chunks of 64 elements = one 128-byte swizzle row:
+//   * A chunk  : 128 rows x 64 bf16, K-major, SWIZZLE_128B - written by 4 producer warps that gather the
+//                fp32 input rows named by the neighbour table (absent -> zeros) with 16-byte loads, split
+//                every value into bf16 hi + bf16 lo and store both images (st.shared.v2 at swizzled offsets).
+//   * B chunk  : COUT rows x 64 bf16 (hi image, lo image), pre-swizzled on the host into exactly this shared
+//                memory image, fetched by ONE cp.async.bulk (TMA) per chunk with an mbarrier transaction count.
+//   * MMA      : one elected thread issues tcgen05.mma kind::f16, 4 K-steps x {hi*hi, lo*hi, hi*lo} per chunk,
+//                FP32 accumulators in TMEM (COUT columns); tcgen05.commit releases the stage.
+//   * epilogue : the 4 producer warps read their TMEM lane quarter with tcgen05.ld, apply the folded
+//                BatchNorm scale/shift (+ReLU) and write the output row once.
+// hi/lo split: a = hi + lo with |a - hi - lo| <= 2^-17 |a|; dropping lo*lo leaves a relative error of ~2^-16 per
+// product, i.e. fp32-class results (the 1e-3 end-to-end budget of the north star needs better than TF32).
+// Chunks in which no row of the tile has a neighbour are skipped entirely (no gather, no TMA, no MMA).
+#include <cuda_bf16.h>
+
+#include "ctx.cuh"
+
+namespace egn {
+
+namespace tc {
+
+constexpr int kRows = 128;           // tile rows (UMMA M)
+constexpr int kChunk = 64;           // K elements per chunk (128 bytes of bf16)
+constexpr int kABytes = kRows * 128; // one A image (hi or lo) of a stage
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4,
+// LBO = 1 (ignored for swizzled K-major), SBO = 1024 B (8 rows x 128 B), version 1, layout type 2.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t umma_idesc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kRows >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// bf16 hi/lo split of 4 floats -> packed hi (2 x u32), lo (2 x u32)
+__device__ __forceinline__ void split4(const float4 v, uint2 &hi, uint2 &lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                      h3 = __float2bfloat16_rn(v.w);
+  const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
+                      l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+  hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+  hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+  lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+}
+
+struct Args {
+  const float *in;
+  float *out;
+  const uint8_t *wpack;  // [n_chunks][hi|lo][COUT][64] bf16, swizzled shared-memory images
+  const float *scale, *shift;
+  int n_out, relu, mode;  // mode 1: 27-neighbour table, 2: 2x2x2 stride-2 children
+  const int *nbr;
+  const int *cstart;
+  const uint32_t *cmask;
+};
+
+template <int CIN, int COUT>
+struct Cfg {
+  static constexpr int kStages = COUT == 128 ? 3 : 4;
+  static constexpr int kBBytes = 2 * COUT * 128;                  // hi + lo image of one weight chunk
+  static constexpr int kStageBytes = 2 * kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + kRows * 27 * 4 + 1024;
+};
+
+template <int CIN, int COUT, int KOFF>
+__global__ void __launch_bounds__(192, 1) k_sconv_tc(Args a) {
+  using C = Cfg<CIN, COUT>;
+  constexpr int kStages = C::kStages;
+  constexpr int NCH = (KOFF * CIN + kChunk - 1) / kChunk;         // chunks if nothing is skipped
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *tiles = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-byte alignment
+  int *s_nbr = (int *)(tiles + kStages * C::kStageBytes);                          // [kRows][KOFF]
+  uint8_t *tail = (uint8_t *)(s_nbr + kRows * 27);
+  uint64_t *full = (uint64_t *)tail;                    // [kStages]
+  uint64_t *empty = full + kStages;                     // [kStages]
+  uint64_t *accum = empty + kStages;                    // [1]
+  uint32_t *s_tmem = (uint32_t *)(accum + 1);
+  int *s_nlist = (int *)(s_tmem + 1);
+  uint32_t *s_present = (uint32_t *)(s_nlist + 1);      // [2] bit j: chunk j has at least one present row
+  int *s_list = (int *)(s_present + 2);                 // [NCH] compacted chunk ids
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * kRows;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 128 + 1);   // 128 gather threads + the TMA thread's arrive.expect_tx
+      mbar_init(&empty[s], 1);        // one tcgen05.commit
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+    s_present[0] = 0u;
+    s_present[1] = 0u;
+  }
+  if (warp == 5) {                    // TMEM: COUT fp32 accumulator columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)COUT));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // neighbour rows of the tile
+  for (int t = tid; t < kRows * KOFF; t += 192) {
+    const int r = t / KOFF, k = t % KOFF, row = row0 + r;
+    int src = -1;
+    if (row < a.n_out) {
+      if (a.mode == 1) src = a.nbr[(int64_t)row * 27 + k];
+      else {
+        const uint32_t m = a.cmask[row];
+        if ((m >> k) & 1u) src = a.cstart[row] + __popc(m & ((1u << k) - 1u));
+      }
+    }
+    s_nbr[r * KOFF + k] = src;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // which chunks have any present row
+  for (int t = tid; t < kRows * KOFF; t += 192) {
+    if (s_nbr[t] >= 0) {
+      const int k = t % KOFF;
+      if (CIN == 128) atomicOr(&s_present[(2 * k) >> 5], 3u << ((2 * k) & 31));       // both halves (2k is even, never straddles)
+      else { const int j = CIN == 64 ? k : (k >> 1); atomicOr(&s_present[j >> 5], 1u << (j & 31)); }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int n = 0;
+    for (int j = 0; j < NCH; ++j)
+      if ((s_present[j >> 5] >> (j & 31)) & 1u) s_list[n++] = j;
+    *s_nlist = n;
+  }
+  __syncthreads();
+  const int nlist = *s_nlist;
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp < 4) {
+    // ===================== A producers: gather + bf16 split =====================
+    const int cidx = tid & 15;             // 16-byte column (4 floats) inside the 64-float chunk row
+    const int rsub = tid >> 4;             // 0..7
+    for (int i = 0; i < nlist; ++i) {
+      const int j = s_list[i];
+      const int s = i % kStages;
+      const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+      int koff, coff;                      // kernel offset and float offset inside the source row for this thread
+      if (CIN == 32) { koff = 2 * j + (cidx >> 3); coff = (cidx & 7) * 4; }
+      else if (CIN == 64) { koff = j; coff = cidx * 4; }
+      else { koff = j >> 1; coff = (j & 1) * 64 + cidx * 4; }
+      float4 v[16];
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const int r = p * 8 + rsub;
+        const int src = (koff < KOFF) ? s_nbr[r * KOFF + koff] : -1;
+        v[p] = src >= 0 ? __ldg((const float4 *)(a.in + (size_t)src * CIN + coff)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      mbar_wait(&empty[s], ph ^ 1u);
+      uint8_t *a_hi = tiles + s * C::kStageBytes, *a_lo = a_hi + kABytes;
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const int r = p * 8 + rsub;
+        uint2 hi, lo;
+        split4(v[p], hi, lo);
+        const int off = r * 128 + (((cidx >> 1) ^ (r & 7)) << 4) + ((cidx & 1) << 3);
+        *(uint2 *)(a_hi + off) = hi;
+        *(uint2 *)(a_lo + off) = lo;
+      }
+      fence_proxy_async();
+      mbar_arrive(&full[s]);
+    }
+    // ===================== epilogue: TMEM -> scale/shift/relu -> global =====================
+    mbar_wait(accum, 0u);
+    tc_fence_after();
+    const int row = row0 + tid;
+#pragma unroll
+    for (int c0 = 0; c0 < COUT; c0 += 32) {
+      uint32_t r[32];
+      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+      if (row < a.n_out) {
+        float *o = a.out + (size_t)row * COUT + c0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float4 y;
+          float *yy = (float *)&y;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c0 + q * 4 + e;
+            float val = __uint_as_float(r[q * 4 + e]);
+            val = val * (a.scale ? __ldg(a.scale + c) : 1.f) + (a.shift ? __ldg(a.shift + c) : 0.f);
+            if (a.relu) val = fmaxf(val, 0.f);
+            yy[e] = val;
+          }
+          *(float4 *)(o + q * 4) = y;
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == 4) {
+    // ===================== B loader: one bulk copy per chunk =====================
+    if (lane == 0) {
+      for (int i = 0; i < nlist; ++i) {
+        const int j = s_list[i];
+        const int s = i % kStages;
+        const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full[s], (uint32_t)C::kBBytes);
+        bulk_g2s(tiles + s * C::kStageBytes + 2 * kABytes, a.wpack + (size_t)j * C::kBBytes, (uint32_t)C::kBBytes, &full[s]);
+      }
+    }
+  } else {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(COUT);
+      for (int i = 0; i < nlist; ++i) {
+        const int s = i % kStages;
+        const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(tiles + s * C::kStageBytes);
+        const uint32_t sb = sa + 2 * kABytes;
+#pragma unroll
+        for (int ks = 0; ks < kChunk / 16; ++ks) {
+          const uint64_t ahi = umma_desc(sa + ks * 32), alo = umma_desc(sa + kABytes + ks * 32);
+          const uint64_t bhi = umma_desc(sb + ks * 32), blo = umma_desc(sb + COUT * 128 + ks * 32);
+          umma_f16(tmem_base, ahi, bhi, idesc, (i | ks) ? 1u : 0u);
+          umma_f16(tmem_base, alo, bhi, idesc, 1u);
+          umma_f16(tmem_base, ahi, blo, idesc, 1u);
+        }
+        umma_commit(&empty[s]);          // stage reusable once these MMAs have read it
+      }
+      umma_commit(accum);                // accumulator complete
+    }
+  }
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)COUT));
+  }
+}
+
+template <int CIN, int COUT, int KOFF>
+static int launch(egn_ctx *ctx, const Args &a, const char *name, double bytes, double flops, cudaStream_t s) {
+  using C = Cfg<CIN, COUT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EGN_CUDA(cudaFuncSetAttribute(k_sconv_tc<CIN, COUT, KOFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_done = true;
+  }
+  const int grid = (int)div_up(a.n_out, kRows);
+  EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv_tc<CIN, COUT, KOFF><<<grid, 192, C::kSmemBytes, s>>>(a));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+
+}  // namespace tc
+
+bool sconv_tc_supported(int ksize, int transposed, int cin, int cout) {
+  if (transposed) return false;
+  if (ksize == 3) return (cin == 32 && (cout == 32 || cout == 64)) || (cin == 64 && (cout == 64 || cout == 128)) || (cin == 128 && cout == 128);
+  if (ksize == 2) return cin == cout && (cin == 32 || cin == 64 || cin == 128);
+  return false;
+}
+
+// packed-weight bytes for a (ksize, cin, cout) convolution: n_chunks * 2 images * cout * 128
+size_t sconv_tc_wpack_bytes(int ksize, int cin, int cout) {
+  const int koff = ksize == 3 ? 27 : 8;
+  return (size_t)((koff * cin + 63) / 64) * 2 * cout * 128;
+}
+
+int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int cin, int cout, const float *in, const void *wpack, const float *scale,
+                const float *shift, int relu, float *out, cudaStream_t s) {
+  const Pyramid &py = ctx->pyr;
+  EGN_CHECK(py.valid, EGN_ERR_STATE, "conv before coords_build");
+  EGN_CHECK(sconv_tc_supported(ksize, 0, cin, cout), EGN_ERR_INVALID, "tensor-core conv: unsupported shape k=%d %d->%d", ksize, cin, cout);
+  EGN_CHECK(((uintptr_t)wpack & 15) == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, EGN_ERR_INVALID,
+            "tensor-core conv: pointers must be 16-byte aligned");
+  tc::Args a = {};
+  a.in = in; a.out = out; a.wpack = (const uint8_t *)wpack; a.scale = scale; a.shift = shift; a.relu = relu;
+  long long pairs;
+  char name[48];
+  if (ksize == 3) {
+    EGN_CHECK(level_in >= 1 && level_in < P, EGN_ERR_INVALID, "conv k=3: bad level");
+    a.mode = 1; a.n_out = py.n[level_in]; a.nbr = py.nbr[level_in];
+    pairs = py.pairs27[level_in];
+    snprintf(name, sizeof(name), "tc_conv3x3x3_c%d_%d", cin, cout);
+  } else {
+    EGN_CHECK(level_in >= 0 && level_in + 1 < P, EGN_ERR_INVALID, "conv k=2: bad level");
+    a.mode = 2; a.n_out = py.n[level_in + 1]; a.cstart = py.cstart[level_in + 1]; a.cmask = py.cmask[level_in + 1];
+    pairs = py.n[level_in];
+    snprintf(name, sizeof(name), "tc_conv2x2x2s2_c%d_%d", cin, cout);
+  }
+  if (a.n_out == 0) return EGN_OK;
+  const int K = ksize == 3 ? 27 : 8;
+  const double bytes = (double)pairs * (cin + cout) * 4 + (double)pairs * 8 + (double)K * cin * cout * 4;
+  const double flops = 2.0 * pairs * cin * cout;
+#define EGN_TC_CASE(CI, CO)                                                                         \
+  if (cin == CI && cout == CO) {                                                                    \
+    if (ksize == 3) return tc::launch<CI, CO, 27>(ctx, a, name, bytes, flops, s);                   \
+    return tc::launch<CI, CO, 8>(ctx, a, name, bytes, flops, s);                                    \
+  }
+  EGN_TC_CASE(32, 32)
+  EGN_TC_CASE(32, 64)
+  EGN_TC_CASE(64, 64)
+  EGN_TC_CASE(64, 128)
+  EGN_TC_CASE(128, 128)
+#undef EGN_TC_CASE
+  EGN_CHECK(false, EGN_ERR_INVALID, "tensor-core conv: no kernel instance");
+}
+
+}  // namespace egn

@@ -23,7 +23,8 @@ class CoordsInfo(C.Structure):
 
 
 class Layer(C.Structure):
-    _fields_ = [("cin", C.c_int32), ("cout", C.c_int32), ("w", C.c_int64), ("scale", C.c_int64), ("shift", C.c_int64)]
+    _fields_ = [("cin", C.c_int32), ("cout", C.c_int32), ("w", C.c_int64), ("scale", C.c_int64), ("shift", C.c_int64),
+                ("wtc", C.c_int64)]
 
 
 class Head(C.Structure):
@@ -61,6 +62,8 @@ _SIGNATURES = {
     "egn_forward": (C.c_int, [_P, C.POINTER(Net), _P, _P, _P, _P, _P, _P, _P]),
     "egn_forward_tap": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "egn_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
+    "egn_conv_tc": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P]),
+    "egn_set_tensor_cores": (C.c_int, [_P, C.c_int]),
     "egn_global_pool": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "egn_broadcast_mul": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "egn_profile_enable": (C.c_int, [_P, C.c_int]),

@@ -37,17 +37,46 @@ def _bn_fold(sd, prefix, eps=1e-5):
     return scale, b - m * scale
 
 
+TC_SHAPES = {27: {(32, 32), (32, 64), (64, 64), (64, 128), (128, 128)}, 8: {(32, 32), (64, 64), (128, 128)}}
+
+
+def pack_tc(kernel: torch.Tensor) -> torch.Tensor:
+    """(K, Cin, Cout) f32 kernel -> the tensor-core image of ``egn_conv_tc`` as a flat bf16 tensor:
+    [ceil(K*Cin/64)][hi|lo][Cout][64] with the 16-byte groups of row n XOR-swizzled by (n & 7) - byte for byte the
+    SWIZZLE_128B K-major shared-memory tile that ``tcgen05.mma`` reads, so the kernel fetches a chunk with one
+    bulk copy.  hi = bf16(w), lo = bf16(w - hi): w ~ hi + lo to 2^-17 relative."""
+    K, cin, cout = kernel.shape
+    flat = kernel.detach().to(torch.float32).cpu().reshape(K * cin, cout)
+    nch = (K * cin + 63) // 64
+    pad = nch * 64 - K * cin
+    if pad:
+        flat = torch.cat([flat, torch.zeros(pad, cout)], dim=0)
+    hi = flat.to(torch.bfloat16)
+    lo = (flat - hi.to(torch.float32)).to(torch.bfloat16)
+    n = torch.arange(cout)
+    g = torch.arange(8)
+    src_group = g[None, :] ^ (n[:, None] & 7)                                  # stored group g' holds source group g' ^ (n & 7)
+    images = []
+    for part in (hi, lo):
+        t = part.reshape(nch, 64, cout).permute(0, 2, 1).reshape(nch, cout, 8, 8)   # [chunk][n][group][elem]
+        idx = src_group[None, :, :, None].expand(nch, cout, 8, 8)
+        images.append(torch.gather(t, 2, idx))
+    return torch.stack(images, dim=1).reshape(-1).contiguous()                 # [nch][2][cout][64]
+
+
 def _conv(blob, kernel, bn=None) -> L.Layer:
     k = kernel if kernel.dim() == 3 else kernel.unsqueeze(0)
-    lay = L.Layer(cin=k.shape[1], cout=k.shape[2], w=blob.add(k), scale=-1, shift=-1)
+    lay = L.Layer(cin=k.shape[1], cout=k.shape[2], w=blob.add(k), scale=-1, shift=-1, wtc=-1)
     if bn is not None:
         lay.scale, lay.shift = blob.add(bn[0]), blob.add(bn[1])
+    if (k.shape[1], k.shape[2]) in TC_SHAPES.get(k.shape[0], ()):
+        lay.wtc = blob.add(pack_tc(k).view(torch.float32))                     # bf16 pairs stored in f32 slots
     return lay
 
 
 def _linear(blob, sd, prefix) -> L.Layer:
     w = sd[prefix + ".linear.weight"]                     # (out, in)
-    lay = L.Layer(cin=w.shape[1], cout=w.shape[0], w=blob.add(w.t()), scale=-1, shift=-1)
+    lay = L.Layer(cin=w.shape[1], cout=w.shape[0], w=blob.add(w.t()), scale=-1, shift=-1, wtc=-1)
     if prefix + ".linear.bias" in sd:
         lay.shift = blob.add(sd[prefix + ".linear.bias"])
     return lay

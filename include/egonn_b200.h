@@ -100,6 +100,7 @@ typedef struct {
   int64_t w;      /* (K,cin,cout) kernel, K = 125/27/8/1 */
   int64_t scale;  /* (cout) folded eval-mode BatchNorm scale gamma/sqrt(var+eps), or -1 */
   int64_t shift;  /* (cout) folded BatchNorm shift / Linear bias, or -1 */
+  int64_t wtc;    /* tensor-core image of the kernel (egn_conv_tc layout, bf16 hi/lo, offset in floats), or -1 */
 } egn_layer;
 
 typedef struct {
@@ -161,6 +162,16 @@ int egn_forward_tap(egn_ctx *ctx, int which, int level, float *out, egn_stream_t
 int egn_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout,
              const float *in, const float *w, const float *scale, const float *shift, int relu,
              int accumulate, float *out, egn_stream_t stream);
+/* Tensor-core (tcgen05) variant of egn_conv for ksize 3 (cin->cout in {32->32, 32->64, 64->64, 64->128, 128->128})
+ * and ksize 2 stride 2 (cin == cout in {32, 64, 128}).  wpack is the kernel pre-split into bf16 hi/lo and laid out
+ * as the 128-byte-swizzled shared-memory images the kernel loads with one bulk copy per 64-element reduction chunk:
+ * [ceil(K*cin/64)][hi|lo][cout][64] bf16 with 16-byte group g of row n stored at group g ^ (n & 7)
+ * (egonn_b200/weights.py:pack_tc).  Results are fp32-class (bf16x3 split products, FP32 accumulation in TMEM). */
+int egn_conv_tc(egn_ctx *ctx, int level_in, int ksize, int cin, int cout, const float *in, const void *wpack,
+                const float *scale, const float *shift, int relu, float *out, egn_stream_t stream);
+/* 1 (default): egn_forward runs layers that carry a tensor-core image on the tcgen05 path; 0: FP32 CUDA cores only. */
+int egn_set_tensor_cores(egn_ctx *ctx, int enable);
+
 /* Replaces: ME.MinkowskiGlobalPooling / GlobalAvgPooling / GlobalMaxPooling: out (n_batches, c). */
 int egn_global_pool(egn_ctx *ctx, int level, int c, const float *in, int is_max, float *out, egn_stream_t stream);
 /* Replaces: ME.MinkowskiBroadcastMultiplication: out[r] = in[r] * g[batch(r)]. */
