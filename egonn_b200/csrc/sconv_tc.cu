@@ -100,16 +100,23 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// bf16 hi/lo split of 4 floats -> packed hi (2 x u32), lo (2 x u32)
-__device__ __forceinline__ void split4(const float4 v, uint2 &hi, uint2 &lo) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
-                      h3 = __float2bfloat16_rn(v.w);
-  const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
-                      l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
-  hi.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-  hi.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-  lo.x = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-  lo.y = (uint32_t)__bfloat16_as_ushort(l2) | ((uint32_t)__bfloat16_as_ushort(l3) << 16);
+// bf16 hi/lo split of 4 floats -> packed hi (2 x u32), lo (2 x u32); cvt.rn.bf16x2.f32 converts two values at once
+__device__ __forceinline__ void split2(float x, float y, uint32_t &hi, uint32_t &lo) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(x, y);                 // .x (low half) = x
+  hi = *reinterpret_cast<uint32_t *>(&h);
+  const float fx = __uint_as_float(hi << 16), fy = __uint_as_float(hi & 0xffff0000u);
+  __nv_bfloat162 l = __floats2bfloat162_rn(x - fx, y - fy);
+  lo = *reinterpret_cast<uint32_t *>(&l);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
 struct Args {
@@ -123,18 +130,25 @@ struct Args {
   const uint32_t *cmask;
 };
 
+// COUT <= 64: two CTAs per SM (2 stages, 8 producer warps each); COUT == 128: one CTA (3 stages, 16 producer warps)
 template <int CIN, int COUT>
 struct Cfg {
-  static constexpr int kStages = COUT == 128 ? 3 : 4;
+  static constexpr int kStages = COUT == 128 ? 3 : 2;
+  static constexpr int kProducerWarps = COUT == 128 ? 16 : 8;
+  static constexpr int kCtasPerSm = COUT == 128 ? 1 : 2;
+  static constexpr int kThreads = (kProducerWarps + 2) * 32;
   static constexpr int kBBytes = 2 * COUT * 128;                  // hi + lo image of one weight chunk
   static constexpr int kStageBytes = 2 * kABytes + kBBytes;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + kRows * 27 * 4 + 1024;
 };
 
 template <int CIN, int COUT, int KOFF>
-__global__ void __launch_bounds__(192, 1) k_sconv_tc(Args a) {
+__global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCtasPerSm) k_sconv_tc(Args a) {
   using C = Cfg<CIN, COUT>;
   constexpr int kStages = C::kStages;
+  constexpr int NPW = C::kProducerWarps, PT = NPW * 32, NT = C::kThreads;
+  constexpr int F = 2048 / PT;                                    // float4 per producer thread per chunk
+  constexpr int RSTEP = PT / 16;                                  // rows covered per pass
   constexpr int NCH = (KOFF * CIN + kChunk - 1) / kChunk;         // chunks if nothing is skipped
   extern __shared__ uint8_t smem_raw[];
   uint8_t *tiles = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-byte alignment
@@ -153,7 +167,7 @@ __global__ void __launch_bounds__(192, 1) k_sconv_tc(Args a) {
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], 128 + 1);   // 128 gather threads + the TMA thread's arrive.expect_tx
+      mbar_init(&full[s], PT + 1);    // every gather thread + the TMA thread's arrive.expect_tx
       mbar_init(&empty[s], 1);        // one tcgen05.commit
     }
     mbar_init(accum, 1);
@@ -161,12 +175,12 @@ __global__ void __launch_bounds__(192, 1) k_sconv_tc(Args a) {
     s_present[0] = 0u;
     s_present[1] = 0u;
   }
-  if (warp == 5) {                    // TMEM: COUT fp32 accumulator columns
+  if (warp == NPW + 1) {              // TMEM: COUT fp32 accumulator columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)COUT));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // neighbour rows of the tile
-  for (int t = tid; t < kRows * KOFF; t += 192) {
+  for (int t = tid; t < kRows * KOFF; t += NT) {
     const int r = t / KOFF, k = t % KOFF, row = row0 + r;
     int src = -1;
     if (row < a.n_out) {
@@ -181,12 +195,21 @@ __global__ void __launch_bounds__(192, 1) k_sconv_tc(Args a) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // which chunks have any present row
-  for (int t = tid; t < kRows * KOFF; t += 192) {
-    if (s_nbr[t] >= 0) {
-      const int k = t % KOFF;
-      if (CIN == 128) atomicOr(&s_present[(2 * k) >> 5], 3u << ((2 * k) & 31));       // both halves (2k is even, never straddles)
-      else { const int j = CIN == 64 ? k : (k >> 1); atomicOr(&s_present[j >> 5], 1u << (j & 31)); }
+  // which chunks have any present row (one shared-memory atomic per warp and chunk word)
+  {
+    uint32_t m0 = 0u, m1 = 0u;
+    for (int t = tid; t < kRows * KOFF; t += NT) {
+      if (s_nbr[t] >= 0) {
+        const int k = t % KOFF;
+        if (CIN == 128) { const int j = 2 * k; if (j < 32) m0 |= 3u << j; else m1 |= 3u << (j - 32); }
+        else { const int j = CIN == 64 ? k : (k >> 1); if (j < 32) m0 |= 1u << j; else m1 |= 1u << (j - 32); }
+      }
+    }
+    m0 = __reduce_or_sync(0xffffffffu, m0);
+    m1 = __reduce_or_sync(0xffffffffu, m1);
+    if (lane == 0) {
+      if (m0) atomicOr(&s_present[0], m0);
+      if (m1) atomicOr(&s_present[1], m1);
     }
   }
   __syncthreads();
@@ -200,67 +223,87 @@ __global__ void __launch_bounds__(192, 1) k_sconv_tc(Args a) {
   const int nlist = *s_nlist;
   const uint32_t tmem_base = *s_tmem;
 
-  if (warp < 4) {
-    // ===================== A producers: gather + bf16 split =====================
+  if (warp < NPW) {
+    // ===================== A producers: gather + bf16 split, next chunk prefetched in registers =====================
     const int cidx = tid & 15;             // 16-byte column (4 floats) inside the 64-float chunk row
-    const int rsub = tid >> 4;             // 0..7
-    for (int i = 0; i < nlist; ++i) {
-      const int j = s_list[i];
-      const int s = i % kStages;
-      const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+    const int rsub = tid >> 4;             // 0..RSTEP-1
+    float4 v[F];
+    uint32_t pres = 0u;
+    auto issue = [&](int j, float4 (&dst)[F], uint32_t &pm) {
       int koff, coff;                      // kernel offset and float offset inside the source row for this thread
       if (CIN == 32) { koff = 2 * j + (cidx >> 3); coff = (cidx & 7) * 4; }
       else if (CIN == 64) { koff = j; coff = cidx * 4; }
       else { koff = j >> 1; coff = (j & 1) * 64 + cidx * 4; }
-      float4 v[16];
+      pm = 0u;
 #pragma unroll
-      for (int p = 0; p < 16; ++p) {
-        const int r = p * 8 + rsub;
+      for (int p = 0; p < F; ++p) {
+        const int r = p * RSTEP + rsub;
         const int src = (koff < KOFF) ? s_nbr[r * KOFF + koff] : -1;
-        v[p] = src >= 0 ? __ldg((const float4 *)(a.in + (size_t)src * CIN + coff)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (src >= 0) {
+          dst[p] = __ldg((const float4 *)(a.in + (size_t)src * CIN + coff));
+          pm |= 1u << p;
+        }
       }
+    };
+    if (nlist > 0) issue(s_list[0], v, pres);
+    for (int i = 0; i < nlist; ++i) {
+      const int s = i % kStages;
+      const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+      float4 vn[F];
+      uint32_t pres_n = 0u;
+      if (i + 1 < nlist) issue(s_list[i + 1], vn, pres_n);     // loads of the next chunk fly while this one is converted
       mbar_wait(&empty[s], ph ^ 1u);
       uint8_t *a_hi = tiles + s * C::kStageBytes, *a_lo = a_hi + kABytes;
 #pragma unroll
-      for (int p = 0; p < 16; ++p) {
-        const int r = p * 8 + rsub;
-        uint2 hi, lo;
-        split4(v[p], hi, lo);
+      for (int p = 0; p < F; ++p) {
+        const int r = p * RSTEP + rsub;
+        uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
+        if ((pres >> p) & 1u) {
+          split2(v[p].x, v[p].y, hi.x, lo.x);
+          split2(v[p].z, v[p].w, hi.y, lo.y);
+        }
         const int off = r * 128 + (((cidx >> 1) ^ (r & 7)) << 4) + ((cidx & 1) << 3);
         *(uint2 *)(a_hi + off) = hi;
         *(uint2 *)(a_lo + off) = lo;
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
+#pragma unroll
+      for (int p = 0; p < F; ++p) v[p] = vn[p];
+      pres = pres_n;
     }
     // ===================== epilogue: TMEM -> scale/shift/relu -> global =====================
+    // warp w reads TMEM lane quarter (w & 3) and the column group (w >> 2)
+    constexpr int CPW = COUT / (NPW / 4);
     mbar_wait(accum, 0u);
     tc_fence_after();
-    const int row = row0 + tid;
+    const int q = warp & 3, cg = warp >> 2;
+    const int row = row0 + q * 32 + lane;
 #pragma unroll
-    for (int c0 = 0; c0 < COUT; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, r);
+    for (int cc = 0; cc < CPW; cc += 16) {
+      const int c0 = cg * CPW + cc;
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
       if (row < a.n_out) {
         float *o = a.out + (size_t)row * COUT + c0;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
+        for (int g = 0; g < 4; ++g) {
           float4 y;
           float *yy = (float *)&y;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int c = c0 + q * 4 + e;
-            float val = __uint_as_float(r[q * 4 + e]);
+            const int c = c0 + g * 4 + e;
+            float val = __uint_as_float(r[g * 4 + e]);
             val = val * (a.scale ? __ldg(a.scale + c) : 1.f) + (a.shift ? __ldg(a.shift + c) : 0.f);
             if (a.relu) val = fmaxf(val, 0.f);
             yy[e] = val;
           }
-          *(float4 *)(o + q * 4) = y;
+          *(float4 *)(o + g * 4) = y;
         }
       }
     }
     tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == NPW) {
     // ===================== B loader: one bulk copy per chunk =====================
     if (lane == 0) {
       for (int i = 0; i < nlist; ++i) {
@@ -297,7 +340,7 @@ __global__ void __launch_bounds__(192, 1) k_sconv_tc(Args a) {
     }
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == NPW + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)COUT));
   }
@@ -312,7 +355,7 @@ static int launch(egn_ctx *ctx, const Args &a, const char *name, double bytes, d
     attr_done = true;
   }
   const int grid = (int)div_up(a.n_out, kRows);
-  EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv_tc<CIN, COUT, KOFF><<<grid, 192, C::kSmemBytes, s>>>(a));
+  EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv_tc<CIN, COUT, KOFF><<<grid, C::kThreads, C::kSmemBytes, s>>>(a));
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
 }
