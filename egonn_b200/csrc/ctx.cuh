@@ -97,8 +97,8 @@ int op_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const floa
 int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out, cudaStream_t s);
 // sconv_tc.cu
 bool sconv_tc_supported(int ksize, int transposed, int cin, int cout);
-int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int cin, int cout, const float *in, const void *wpack, const float *scale,
-                const float *shift, int relu, float *out, cudaStream_t s);
+int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const void *wpack,
+                const float *scale, const float *shift, int relu, float *out, cudaStream_t s);
 // forward.cu
 int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float *features, float *global_out,
             float *desc_out, float *kp_out, float *sigma_out, cudaStream_t s);

@@ -35,7 +35,7 @@ struct Fwd {
   // conv described by an egn_layer on the pyramid
   int layer(const egn_layer &l, int level_in, int ksize, int transposed, const float *in, int relu, int accumulate, float *out) {
     if (ctx->use_tc && l.wtc >= 0 && !accumulate && sconv_tc_supported(ksize, transposed, l.cin, l.cout))
-      return run_conv_tc(ctx, level_in, ksize, l.cin, l.cout, in, wb + l.wtc, W(l.scale), W(l.shift), relu, out, s);
+      return run_conv_tc(ctx, level_in, ksize, transposed, l.cin, l.cout, in, wb + l.wtc, W(l.scale), W(l.shift), relu, out, s);
     return run_conv(ctx, level_in, ksize, transposed, l.cin, l.cout, in, W(l.w), W(l.scale), W(l.shift), relu, accumulate, out, s);
   }
 };

@@ -12,6 +12,8 @@
 // gathers the input rows named by the neighbour table (absent -> zeros) and accumulates in registers; the
 // output row is written exactly once with the BatchNorm/ReLU/residual epilogue applied - no atomics, no
 // separate scatter pass, deterministic.
+#include <algorithm>
+
 #include "ctx.cuh"
 
 namespace egn {
@@ -176,65 +178,119 @@ __device__ __forceinline__ uint32_t morton6(int x, int y, int z) {  // x,y,z in 
   return (uint32_t)((x & 1) | ((y & 1) << 1) | ((z & 1) << 2) | ((x & 2) << 2) | ((y & 2) << 3) | ((z & 2) << 4));
 }
 
+// Lane = output row.  Phase 1 (divergent, light): every lane walks the <= 8 level-2 cells its window touches,
+// ANDs the cell occupancy with the window box (64-bit masks from a small LUT) and appends (offset index t,
+// feature row) of every present neighbour to its column of a shared-memory list.  Phase 2 (converged, heavy):
+// the warp loops to the longest list; each lane does 32 FMAs per neighbour with the kernel row W[t,:] read as
+// 8 conflict-free LDS.128 (row stride 36 floats).  Work is proportional to the PRESENT pairs (~18 of 125).
+constexpr int kC0Warps = 4;
+constexpr int kC0WStride = 36;
+
 template <int KS>
-__global__ void __launch_bounds__(256) k_conv0(const float *__restrict__ f0 /* (n0) canonical order */, const uint64_t *__restrict__ keys0,
-                                               const int *__restrict__ up0, const int *__restrict__ up1, const int *__restrict__ nbr2,
-                                               const uint64_t *__restrict__ mask64, const int *__restrict__ first0, int n0,
-                                               const float *__restrict__ w /* (KS^3,1,cout) */, const float *__restrict__ scale,
-                                               const float *__restrict__ shift, int cout, int relu, float *__restrict__ out) {
-  constexpr int KV = KS * KS * KS, R = KS / 2, ROUNDS = (KV + 31) / 32;
-  extern __shared__ float s_w0[];  // KV * cout
-  for (int t = threadIdx.x; t < KV * cout; t += blockDim.x) s_w0[t] = w[t];
+__global__ void __launch_bounds__(kC0Warps * 32, 2) k_conv0(const float *__restrict__ f0 /* (n0) canonical order */,
+                                                            const uint64_t *__restrict__ keys0, const int *__restrict__ up0,
+                                                            const int *__restrict__ up1, const int *__restrict__ nbr2,
+                                                            const uint64_t *__restrict__ mask64, const int *__restrict__ first0, int n0,
+                                                            const float *__restrict__ w /* (KS^3,1,32) */, const float *__restrict__ scale,
+                                                            const float *__restrict__ shift, int relu, float *__restrict__ out) {
+  constexpr int KV = KS * KS * KS, R = KS / 2, COUT = 32;
+  extern __shared__ __align__(16) uint8_t s_raw[];
+  float *s_w = (float *)s_raw;                                           // [KV][36]
+  unsigned long long *s_box = (unsigned long long *)(s_w + KV * kC0WStride + 4);   // [axis 3][l 4][delta 3]
+  uint32_t *s_list = (uint32_t *)(s_box + 36);                           // [warp][KV][32]
+  for (int t = threadIdx.x; t < KV * COUT; t += blockDim.x) s_w[(t / COUT) * kC0WStride + (t % COUT)] = w[t];
+  if (threadIdx.x < 36) {
+    // 64-bit set of Morton-6 codes whose `axis` coordinate lies in window(l) /\ cell(delta)
+    const int axis = threadIdx.x / 12, l = (threadIdx.x / 3) % 4, d = threadIdx.x % 3 - 1;
+    const unsigned long long b0[3] = {0xAAAAAAAAAAAAAAAAull, 0xCCCCCCCCCCCCCCCCull, 0xF0F0F0F0F0F0F0F0ull};   // low coordinate bit = 1
+    const unsigned long long b1[3] = {0xFF00FF00FF00FF00ull, 0xFFFF0000FFFF0000ull, 0xFFFFFFFF00000000ull};   // high coordinate bit = 1
+    unsigned long long m = 0ull;
+    for (int p = 0; p < 4; ++p) {
+      const int g = p + 4 * d;                                           // coordinate relative to the own cell origin
+      if (g >= l - R && g <= l + R)
+        m |= ((p & 1) ? b0[axis] : ~b0[axis]) & ((p & 2) ? b1[axis] : ~b1[axis]);
+    }
+    s_box[threadIdx.x] = m;
+  }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const int warps = (gridDim.x * blockDim.x) >> 5;
-  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n0; r += warps) {
-    const uint32_t m = (uint32_t)(keys0[r] & 63ull);
-    const int lx = (m & 1) | ((m >> 2) & 2), ly = ((m >> 1) & 1) | ((m >> 3) & 2), lz = ((m >> 2) & 1) | ((m >> 4) & 2);
-    const int cell = up1[up0[r]];
-    // lanes 0..26 hold the occupancy word / first row of the 27 neighbouring level-2 cells
-    unsigned long long occ = 0ull;
-    int base = 0;
-    if (lane < 27) {
-      const int q = nbr2[(int64_t)cell * 27 + lane];
-      if (q >= 0) { occ = mask64[q]; base = first0[q]; }
-    }
-    const uint32_t occ_lo = (uint32_t)occ, occ_hi = (uint32_t)(occ >> 32);
-    float fval[ROUNDS];
-    uint32_t pres[ROUNDS];
-#pragma unroll
-    for (int rd = 0; rd < ROUNDS; ++rd) {
-      const int t = rd * 32 + lane;
-      const int tt = t < KV ? t : 0;
-      const int px = lx + (tt % KS) - R, py = ly + (tt / KS) % KS - R, pz = lz + tt / (KS * KS) - R;
-      const int j = ((px >> 2) + 1) + 3 * ((py >> 2) + 1) + 9 * ((pz >> 2) + 1);
-      const uint32_t bit = morton6(px & 3, py & 3, pz & 3);
-      const uint32_t lo = __shfl_sync(0xffffffffu, occ_lo, j), hi = __shfl_sync(0xffffffffu, occ_hi, j);
-      const int b0 = __shfl_sync(0xffffffffu, base, j);
-      const unsigned long long o = ((unsigned long long)hi << 32) | lo;
-      const bool p = t < KV && ((o >> bit) & 1ull);
-      fval[rd] = p ? f0[b0 + __popcll(o & ((1ull << bit) - 1ull))] : 0.f;
-      pres[rd] = __ballot_sync(0xffffffffu, p);
-    }
-    for (int c0 = 0; c0 < cout; c0 += 32) {
-      const int c = c0 + lane;
-      float acc = 0.f;
-#pragma unroll
-      for (int rd = 0; rd < ROUNDS; ++rd) {
-        uint32_t bal = pres[rd];
-        while (bal) {
-          const int src = __ffs(bal) - 1;
-          bal &= bal - 1;
-          const float f = __shfl_sync(0xffffffffu, fval[rd], src);
-          if (c < cout) acc = fmaf(f, s_w0[(rd * 32 + src) * cout + c], acc);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t *list = s_list + (size_t)warp * KV * 32;
+  const int nwarps = gridDim.x * kC0Warps;
+  for (int base = (blockIdx.x * kC0Warps + warp) * 32; base < n0; base += nwarps * 32) {
+    const int r = base + lane;
+    int cnt = 0;
+    if (r < n0) {
+      const uint32_t m = (uint32_t)(keys0[r] & 63ull);
+      const int lx = (m & 1) | ((m >> 2) & 2), ly = ((m >> 1) & 1) | ((m >> 3) & 2), lz = ((m >> 2) & 1) | ((m >> 4) & 2);
+      const int cell = up1[up0[r]];
+      const int *nb = nbr2 + (int64_t)cell * 27;
+#pragma unroll 1
+      for (int dz = -1; dz <= 1; ++dz) {
+        const unsigned long long bz = s_box[24 + lz * 3 + dz + 1];
+        if (!bz) continue;
+#pragma unroll 1
+        for (int dy = -1; dy <= 1; ++dy) {
+          const unsigned long long byz = bz & s_box[12 + ly * 3 + dy + 1];
+          if (!byz) continue;
+#pragma unroll 1
+          for (int dx = -1; dx <= 1; ++dx) {
+            const unsigned long long box = byz & s_box[lx * 3 + dx + 1];
+            if (!box) continue;
+            const int q = nb[(dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)];
+            if (q < 0) continue;
+            const unsigned long long occ = mask64[q];
+            unsigned long long pm = occ & box;
+            const int fb = first0[q];
+            while (pm) {
+              const int b = __ffsll((long long)pm) - 1;
+              pm &= pm - 1;
+              const int x = (b & 1) | ((b >> 2) & 2), y = ((b >> 1) & 1) | ((b >> 3) & 2), z = ((b >> 2) & 1) | ((b >> 4) & 2);
+              const int t = (x + 4 * dx - lx + R) + KS * ((y + 4 * dy - ly + R) + KS * (z + 4 * dz - lz + R));
+              const int frow = fb + __popcll(occ & ((1ull << b) - 1ull));
+              list[cnt * 32 + lane] = (uint32_t)t | ((uint32_t)frow << 7);
+              ++cnt;
+            }
+          }
         }
       }
-      if (c < cout) {
-        float v = acc * (scale ? scale[c] : 1.f) + (shift ? shift[c] : 0.f);
-        if (relu) v = fmaxf(v, 0.f);
-        out[(size_t)r * cout + c] = v;
+    }
+    __syncwarp();
+    const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+    for (int i = 0; i < maxcnt; ++i) {
+      if (i < cnt) {
+        const uint32_t e = list[i * 32 + lane];
+        const float f = f0[e >> 7];
+        const float4 *wr = (const float4 *)(s_w + (e & 127u) * kC0WStride);
+#pragma unroll
+        for (int c4 = 0; c4 < COUT / 4; ++c4) {
+          const float4 ww = wr[c4];
+          acc[c4 * 4 + 0] = fmaf(f, ww.x, acc[c4 * 4 + 0]);
+          acc[c4 * 4 + 1] = fmaf(f, ww.y, acc[c4 * 4 + 1]);
+          acc[c4 * 4 + 2] = fmaf(f, ww.z, acc[c4 * 4 + 2]);
+          acc[c4 * 4 + 3] = fmaf(f, ww.w, acc[c4 * 4 + 3]);
+        }
       }
     }
+    if (r < n0) {
+      float4 *o = (float4 *)(out + (size_t)r * COUT);
+#pragma unroll
+      for (int c4 = 0; c4 < COUT / 4; ++c4) {
+        float4 y;
+        float *yy = (float *)&y;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int c = c4 * 4 + e;
+          float v = acc[c] * (scale ? __ldg(scale + c) : 1.f) + (shift ? __ldg(shift + c) : 0.f);
+          if (relu) v = fmaxf(v, 0.f);
+          yy[e] = v;
+        }
+        o[c4] = y;
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -427,22 +483,24 @@ int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const fl
               int relu, float *out, cudaStream_t s) {
   const Pyramid &py = ctx->pyr;
   EGN_CHECK(ksize == 5 || ksize == 3, EGN_ERR_INVALID, "conv0: kernel size %d not supported (3 or 5)", ksize);
+  EGN_CHECK(cout == 32, EGN_ERR_INVALID, "conv0: %d output channels not supported (the egonn / MinkLoc3D stems use 32)", cout);
   const int n0 = py.n[0];
-  const int threads = 256, blocks = grid_for((int64_t)n0 * 32, threads, 16);
+  EGN_CHECK(n0 <= (1 << 25), EGN_ERR_INVALID, "conv0: more than 2^25 voxels");
+  const int kv = ksize * ksize * ksize;
+  const size_t smem = (size_t)(kv * kC0WStride + 4) * 4 + 36 * 8 + (size_t)kC0Warps * kv * 32 * 4;
+  const int blocks = (int)std::min<int64_t>(div_up(n0, kC0Warps * 32), (int64_t)kNumSMs * 2 * 4);
   const double pairs = (double)py.pairs_conv0;  // profile mode only (0 otherwise)
-  const double bytes = pairs * (1 + cout) * 4 + pairs * 8 + (double)ksize * ksize * ksize * cout * 4, flops = 2.0 * pairs * cout;
+  const double bytes = pairs * (1 + cout) * 4 + pairs * 8 + (double)kv * cout * 4, flops = 2.0 * pairs * cout;
   if (ksize == 5) {
-    const size_t smem = (size_t)125 * cout * 4;
-    EGN_CHECK(smem <= 200 * 1024, EGN_ERR_INVALID, "conv0: cout too large");
-    if (smem > 48 * 1024) EGN_CUDA(cudaFuncSetAttribute(k_conv0<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static bool attr = false;
+    if (!attr) { EGN_CUDA(cudaFuncSetAttribute(k_conv0<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     EGN_LAUNCH(ctx, "conv0_5x5x5", bytes, flops, s,
-               k_conv0<5><<<blocks, threads, smem, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], py.mask64, py.first0, n0, w,
-                                                         scale, shift, cout, relu, out));
+               k_conv0<5><<<blocks, kC0Warps * 32, smem, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], py.mask64, py.first0, n0, w,
+                                                              scale, shift, relu, out));
   } else {
-    const size_t smem = (size_t)27 * cout * 4;
     EGN_LAUNCH(ctx, "conv0_3x3x3", bytes, flops, s,
-               k_conv0<3><<<blocks, threads, smem, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], py.mask64, py.first0, n0, w,
-                                                         scale, shift, cout, relu, out));
+               k_conv0<3><<<blocks, kC0Warps * 32, smem, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], py.mask64, py.first0, n0, w,
+                                                              scale, shift, relu, out));
   }
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
@@ -492,7 +550,7 @@ int op_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int 
 }
 
 static int pool_slices(int n_rows, int n_batches) {
-  int s = (int)div_up(n_rows, (int64_t)n_batches * 256);
+  int s = (int)div_up(n_rows, (int64_t)n_batches * 48);
   return s < 1 ? 1 : (s > 64 ? 64 : s);
 }
 

@@ -124,10 +124,12 @@ struct Args {
   float *out;
   const uint8_t *wpack;  // [n_chunks][hi|lo][COUT][64] bf16, swizzled shared-memory images
   const float *scale, *shift;
-  int n_out, relu, mode;  // mode 1: 27-neighbour table, 2: 2x2x2 stride-2 children
+  int n_out, relu, mode;  // mode 1: 27-neighbour table, 2: 2x2x2 stride-2 children, 3: transposed 2x2x2 (parent, slice = own code)
   const int *nbr;
   const int *cstart;
   const uint32_t *cmask;
+  const int *up;           // mode 3: parent row of every output (fine) row
+  const uint64_t *keys;    // mode 3: key of every output row (kernel slice = key & 7)
 };
 
 // COUT <= 64: two CTAs per SM (2 stages, 8 producer warps each); COUT == 128: one CTA (3 stages, 16 producer warps)
@@ -185,9 +187,11 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     int src = -1;
     if (row < a.n_out) {
       if (a.mode == 1) src = a.nbr[(int64_t)row * 27 + k];
-      else {
+      else if (a.mode == 2) {
         const uint32_t m = a.cmask[row];
         if ((m >> k) & 1u) src = a.cstart[row] + __popc(m & ((1u << k) - 1u));
+      } else {
+        if ((int)(a.keys[row] & 7ull) == k) src = a.up[row];
       }
     }
     s_nbr[r * KOFF + k] = src;
@@ -363,7 +367,7 @@ static int launch(egn_ctx *ctx, const Args &a, const char *name, double bytes, d
 }  // namespace tc
 
 bool sconv_tc_supported(int ksize, int transposed, int cin, int cout) {
-  if (transposed) return false;
+  if (transposed) return ksize == 2 && cin == cout && (cin == 32 || cin == 64 || cin == 128);
   if (ksize == 3) return (cin == 32 && (cout == 32 || cout == 64)) || (cin == 64 && (cout == 64 || cout == 128)) || (cin == 128 && cout == 128);
   if (ksize == 2) return cin == cout && (cin == 32 || cin == 64 || cin == 128);
   return false;
@@ -375,11 +379,11 @@ size_t sconv_tc_wpack_bytes(int ksize, int cin, int cout) {
   return (size_t)((koff * cin + 63) / 64) * 2 * cout * 128;
 }
 
-int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int cin, int cout, const float *in, const void *wpack, const float *scale,
-                const float *shift, int relu, float *out, cudaStream_t s) {
+int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const void *wpack,
+                const float *scale, const float *shift, int relu, float *out, cudaStream_t s) {
   const Pyramid &py = ctx->pyr;
   EGN_CHECK(py.valid, EGN_ERR_STATE, "conv before coords_build");
-  EGN_CHECK(sconv_tc_supported(ksize, 0, cin, cout), EGN_ERR_INVALID, "tensor-core conv: unsupported shape k=%d %d->%d", ksize, cin, cout);
+  EGN_CHECK(sconv_tc_supported(ksize, transposed, cin, cout), EGN_ERR_INVALID, "tensor-core conv: unsupported shape k=%d %d->%d", ksize, cin, cout);
   EGN_CHECK(((uintptr_t)wpack & 15) == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, EGN_ERR_INVALID,
             "tensor-core conv: pointers must be 16-byte aligned");
   tc::Args a = {};
@@ -391,6 +395,11 @@ int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int cin, int cout, const 
     a.mode = 1; a.n_out = py.n[level_in]; a.nbr = py.nbr[level_in];
     pairs = py.pairs27[level_in];
     snprintf(name, sizeof(name), "tc_conv3x3x3_c%d_%d", cin, cout);
+  } else if (transposed) {
+    EGN_CHECK(level_in >= 1 && level_in < P, EGN_ERR_INVALID, "transposed conv: bad level");
+    a.mode = 3; a.n_out = py.n[level_in - 1]; a.up = py.up[level_in - 1]; a.keys = py.keys[level_in - 1];
+    pairs = a.n_out;
+    snprintf(name, sizeof(name), "tc_tconv2x2x2s2_c%d_%d", cin, cout);
   } else {
     EGN_CHECK(level_in >= 0 && level_in + 1 < P, EGN_ERR_INVALID, "conv k=2: bad level");
     a.mode = 2; a.n_out = py.n[level_in + 1]; a.cstart = py.cstart[level_in + 1]; a.cmask = py.cmask[level_in + 1];

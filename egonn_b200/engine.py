@@ -171,16 +171,16 @@ class Engine:
         return out
 
     def conv_tc(self, level_in: int, ksize: int, x: torch.Tensor, kernel: torch.Tensor, scale=None, shift=None,
-                relu=False) -> torch.Tensor:
+                relu=False, transposed=False) -> torch.Tensor:
         """tcgen05 path of one convolution (ksize 3, or 2 with stride 2); packs the kernel on the fly."""
         from .weights import pack_tc
         _need_cuda(x, "features")
         cin, cout = kernel.shape[1], kernel.shape[2]
         x = x.detach().to(torch.float32).contiguous()
         wpack = pack_tc(kernel).to(x.device)
-        lvl_out = level_in + 1 if ksize == 2 else level_in
+        lvl_out = (level_in - 1 if transposed else level_in + 1) if ksize == 2 else level_in
         out = self._new((self.info.n_rows[lvl_out], cout), torch.float32)
-        L.check(self.lib.egn_conv_tc(self._ctx, level_in, ksize, cin, cout, _ptr(x), _ptr(wpack), _ptr(scale), _ptr(shift),
+        L.check(self.lib.egn_conv_tc(self._ctx, level_in, ksize, int(transposed), cin, cout, _ptr(x), _ptr(wpack), _ptr(scale), _ptr(shift),
                                      int(relu), _ptr(out), _stream()))
         return out
 

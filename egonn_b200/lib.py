@@ -62,7 +62,7 @@ _SIGNATURES = {
     "egn_forward": (C.c_int, [_P, C.POINTER(Net), _P, _P, _P, _P, _P, _P, _P]),
     "egn_forward_tap": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "egn_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
-    "egn_conv_tc": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P]),
+    "egn_conv_tc": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, _P, _P]),
     "egn_set_tensor_cores": (C.c_int, [_P, C.c_int]),
     "egn_global_pool": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "egn_broadcast_mul": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),

@@ -163,11 +163,11 @@ int egn_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int
              const float *in, const float *w, const float *scale, const float *shift, int relu,
              int accumulate, float *out, egn_stream_t stream);
 /* Tensor-core (tcgen05) variant of egn_conv for ksize 3 (cin->cout in {32->32, 32->64, 64->64, 64->128, 128->128})
- * and ksize 2 stride 2 (cin == cout in {32, 64, 128}).  wpack is the kernel pre-split into bf16 hi/lo and laid out
+ * and ksize 2 stride 2, plain or transposed (cin == cout in {32, 64, 128}).  wpack is the kernel pre-split into bf16 hi/lo and laid out
  * as the 128-byte-swizzled shared-memory images the kernel loads with one bulk copy per 64-element reduction chunk:
  * [ceil(K*cin/64)][hi|lo][cout][64] bf16 with 16-byte group g of row n stored at group g ^ (n & 7)
  * (egonn_b200/weights.py:pack_tc).  Results are fp32-class (bf16x3 split products, FP32 accumulation in TMEM). */
-int egn_conv_tc(egn_ctx *ctx, int level_in, int ksize, int cin, int cout, const float *in, const void *wpack,
+int egn_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const void *wpack,
                 const float *scale, const float *shift, int relu, float *out, egn_stream_t stream);
 /* 1 (default): egn_forward runs layers that carry a tensor-core image on the tcgen05 path; 0: FP32 CUDA cores only. */
 int egn_set_tensor_cores(egn_ctx *ctx, int enable);

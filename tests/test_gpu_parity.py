@@ -283,3 +283,21 @@ def test_forward_tensor_core_and_fp32_paths_agree(cuda, weights):
     model._engine.set_tensor_cores(True)
     for k in ("global", "descriptors", "keypoints", "sigma"):
         assert_close_rel(a[k], b[k], 1e-4, k)
+
+
+@pytest.mark.parametrize("c", [64, 128])
+def test_tensor_core_transposed_conv(c, cuda):
+    """Transposed 2x2x2 stride-2 convolution on the tcgen05 kernel (parent gather, slice = the row's own code)
+    vs the FP32 CUDA-core path."""
+    import egonn_b200 as E
+    g = load_golden("mini3_cartesian")
+    eng = E.Engine(cuda)
+    info = eng.build(torch.from_numpy(g["coords"]).to(cuda))
+    torch.manual_seed(c)
+    for level in (2, 4):
+        x = torch.randn(info.n_rows[level], c, device=cuda)
+        w = torch.randn(8, c, c, device=cuda) / np.sqrt(c)
+        y_tc = eng.conv_tc(level, 2, x, w, transposed=True)
+        y_f32 = eng.conv(level, 2, True, x, w)
+        assert y_tc.shape == (info.n_rows[level - 1], c)
+        assert_close_rel(y_tc, y_f32, 2e-5, f"tconv level {level}")
