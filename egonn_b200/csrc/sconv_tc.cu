@@ -42,15 +42,15 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   uint32_t done;
-  do {
+  do {   // try_wait suspends the thread in hardware until the phase flips or the hint (ns) expires - no busy polling
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t"
         "}"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
   } while (!done);
 }
@@ -100,13 +100,27 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// bf16 hi/lo split of 4 floats -> packed hi (2 x u32), lo (2 x u32); cvt.rn.bf16x2.f32 converts two values at once
+// bf16 hi/lo split: cvt.rn.bf16x2.f32 converts two values at once; lo = bf16(x - float(hi))
 __device__ __forceinline__ void split2(float x, float y, uint32_t &hi, uint32_t &lo) {
   __nv_bfloat162 h = __floats2bfloat162_rn(x, y);                 // .x (low half) = x
   hi = *reinterpret_cast<uint32_t *>(&h);
   const float fx = __uint_as_float(hi << 16), fy = __uint_as_float(hi & 0xffff0000u);
   __nv_bfloat162 l = __floats2bfloat162_rn(x - fx, y - fy);
   lo = *reinterpret_cast<uint32_t *>(&l);
+}
+// 32-byte gather of 8 consecutive floats, predicated (no branch): zeros when the neighbour is absent
+__device__ __forceinline__ void ldg8_pred(const float *p, bool pred, float4 &a, float4 &b) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %9, 0;\n\t"
+      "mov.b32 %0, 0; mov.b32 %1, 0; mov.b32 %2, 0; mov.b32 %3, 0;\n\t"
+      "mov.b32 %4, 0; mov.b32 %5, 0; mov.b32 %6, 0; mov.b32 %7, 0;\n\t"
+      "@q ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%8];\n\t"
+      "@q ld.global.nc.v4.f32 {%4, %5, %6, %7}, [%8+16];\n\t"
+      "}"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p), "r"((uint32_t)pred));
 }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
@@ -141,7 +155,7 @@ struct Cfg {
   static constexpr int kThreads = (kProducerWarps + 2) * 32;
   static constexpr int kBBytes = 2 * COUT * 128;                  // hi + lo image of one weight chunk
   static constexpr int kStageBytes = 2 * kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + kRows * 27 * 4 + 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kRows * 27 * 4 + 2 * COUT * 4 + 512;
 };
 
 template <int CIN, int COUT, int KOFF>
@@ -149,25 +163,29 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   using C = Cfg<CIN, COUT>;
   constexpr int kStages = C::kStages;
   constexpr int NPW = C::kProducerWarps, PT = NPW * 32, NT = C::kThreads;
-  constexpr int F = 2048 / PT;                                    // float4 per producer thread per chunk
-  constexpr int RSTEP = PT / 16;                                  // rows covered per pass
+  constexpr int RSTEP = PT / 8;                                   // 8 threads per row, 8 elements (one 16-byte bf16 group) each
+  constexpr int F = kRows / RSTEP;                                // row slots per producer thread per chunk
   constexpr int NCH = (KOFF * CIN + kChunk - 1) / kChunk;         // chunks if nothing is skipped
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *tiles = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B needs 1024-byte alignment
-  int *s_nbr = (int *)(tiles + kStages * C::kStageBytes);                          // [kRows][KOFF]
-  uint8_t *tail = (uint8_t *)(s_nbr + kRows * 27);
-  uint64_t *full = (uint64_t *)tail;                    // [kStages]
-  uint64_t *empty = full + kStages;                     // [kStages]
-  uint64_t *accum = empty + kStages;                    // [1]
+  constexpr int NBR_ITERS = (kRows * KOFF + NT - 1) / NT;
+  // dynamic shared memory starts 1024-byte aligned (checked below): SWIZZLE_128B tiles need it
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *tiles = smem;
+  int *s_nbr = (int *)(smem + kStages * C::kStageBytes);          // [kRows][KOFF]
+  float *s_scale = (float *)(s_nbr + kRows * 27);                 // [COUT]
+  float *s_shift = s_scale + COUT;                                // [COUT]
+  uint64_t *full = (uint64_t *)(s_shift + COUT);                  // [kStages]
+  uint64_t *empty = full + kStages;                               // [kStages]
+  uint64_t *accum = empty + kStages;                              // [1]
   uint32_t *s_tmem = (uint32_t *)(accum + 1);
   int *s_nlist = (int *)(s_tmem + 1);
-  uint32_t *s_present = (uint32_t *)(s_nlist + 1);      // [2] bit j: chunk j has at least one present row
-  int *s_list = (int *)(s_present + 2);                 // [NCH] compacted chunk ids
+  uint32_t *s_present = (uint32_t *)(s_nlist + 1);                // [2] bit j: chunk j has at least one present row
+  int *s_list = (int *)(s_present + 2);                           // [NCH] compacted chunk ids
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kRows;
 
   if (tid == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], PT + 1);    // every gather thread + the TMA thread's arrive.expect_tx
       mbar_init(&empty[s], 1);        // one tcgen05.commit
@@ -181,32 +199,41 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)COUT));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // neighbour rows of the tile
-  for (int t = tid; t < kRows * KOFF; t += NT) {
-    const int r = t / KOFF, k = t % KOFF, row = row0 + r;
-    int src = -1;
-    if (row < a.n_out) {
-      if (a.mode == 1) src = a.nbr[(int64_t)row * 27 + k];
-      else if (a.mode == 2) {
-        const uint32_t m = a.cmask[row];
-        if ((m >> k) & 1u) src = a.cstart[row] + __popc(m & ((1u << k) - 1u));
-      } else {
-        if ((int)(a.keys[row] & 7ull) == k) src = a.up[row];
+  for (int c = tid; c < COUT; c += NT) {
+    s_scale[c] = a.scale ? a.scale[c] : 1.f;
+    s_shift[c] = a.shift ? a.shift[c] : 0.f;
+  }
+  __syncthreads();                    // s_present zeroed before the atomics below
+  // neighbour rows of the tile: all global loads first, then the shared stores (one latency, not NBR_ITERS)
+  {
+    int src[NBR_ITERS];
+#pragma unroll
+    for (int it = 0; it < NBR_ITERS; ++it) {
+      const int t = tid + it * NT;
+      const int r = t / KOFF, k = t - r * KOFF, row = row0 + r;
+      src[it] = -1;
+      if (t < kRows * KOFF && row < a.n_out) {
+        if (a.mode == 1) src[it] = __ldg(a.nbr + (int64_t)row0 * 27 + t);
+        else if (a.mode == 2) {
+          const uint32_t m = __ldg(a.cmask + row);
+          if ((m >> k) & 1u) src[it] = __ldg(a.cstart + row) + __popc(m & ((1u << k) - 1u));
+        } else {
+          if ((int)(__ldg(a.keys + row) & 7ull) == k) src[it] = __ldg(a.up + row);
+        }
       }
     }
-    s_nbr[r * KOFF + k] = src;
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  // which chunks have any present row (one shared-memory atomic per warp and chunk word)
-  {
     uint32_t m0 = 0u, m1 = 0u;
-    for (int t = tid; t < kRows * KOFF; t += NT) {
-      if (s_nbr[t] >= 0) {
-        const int k = t % KOFF;
-        if (CIN == 128) { const int j = 2 * k; if (j < 32) m0 |= 3u << j; else m1 |= 3u << (j - 32); }
-        else { const int j = CIN == 64 ? k : (k >> 1); if (j < 32) m0 |= 1u << j; else m1 |= 1u << (j - 32); }
+#pragma unroll
+    for (int it = 0; it < NBR_ITERS; ++it) {
+      const int t = tid + it * NT;
+      if (t < kRows * KOFF) {
+        s_nbr[t] = src[it];
+        if (src[it] >= 0) {
+          const int k = t % KOFF;
+          const int j = CIN == 128 ? 2 * k : (CIN == 64 ? k : (k >> 1));
+          const uint32_t bits = CIN == 128 ? 3u : 1u;
+          if (j < 32) m0 |= bits << j; else m1 |= bits << (j - 32);
+        }
       }
     }
     m0 = __reduce_or_sync(0xffffffffu, m0);
@@ -216,7 +243,9 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
       if (m1) atomicOr(&s_present[1], m1);
     }
   }
+  tc_fence_before();
   __syncthreads();
+  tc_fence_after();
   if (tid == 0) {
     int n = 0;
     for (int j = 0; j < NCH; ++j)
@@ -229,52 +258,48 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
 
   if (warp < NPW) {
     // ===================== A producers: gather + bf16 split, next chunk prefetched in registers =====================
-    const int cidx = tid & 15;             // 16-byte column (4 floats) inside the 64-float chunk row
-    const int rsub = tid >> 4;             // 0..RSTEP-1
-    float4 v[F];
-    uint32_t pres = 0u;
-    auto issue = [&](int j, float4 (&dst)[F], uint32_t &pm) {
+    // thread -> (row slot rs, 16-byte group g): rows r = p*RSTEP + rs share (r & 7) = (rs & 7), so the swizzled
+    // byte offset inside a row is a per-thread constant and every row offset is an immediate.
+    const int g = tid & 7, rs = tid >> 3;
+    const int sw_off = rs * 128 + ((g ^ (rs & 7)) << 4);
+    const int *my_nbr = s_nbr + rs * KOFF;
+    float4 va[F], vb[F];
+    auto issue = [&](int j, float4 (&da)[F], float4 (&db)[F]) {
       int koff, coff;                      // kernel offset and float offset inside the source row for this thread
-      if (CIN == 32) { koff = 2 * j + (cidx >> 3); coff = (cidx & 7) * 4; }
-      else if (CIN == 64) { koff = j; coff = cidx * 4; }
-      else { koff = j >> 1; coff = (j & 1) * 64 + cidx * 4; }
-      pm = 0u;
+      if (CIN == 32) { koff = 2 * j + (g >> 2); coff = (g & 3) * 8; }
+      else if (CIN == 64) { koff = j; coff = g * 8; }
+      else { koff = j >> 1; coff = (j & 1) * 64 + g * 8; }
+      const bool kvalid = koff < KOFF;
+      if (!kvalid) koff = 0;
 #pragma unroll
       for (int p = 0; p < F; ++p) {
-        const int r = p * RSTEP + rsub;
-        const int src = (koff < KOFF) ? s_nbr[r * KOFF + koff] : -1;
-        if (src >= 0) {
-          dst[p] = __ldg((const float4 *)(a.in + (size_t)src * CIN + coff));
-          pm |= 1u << p;
-        }
+        const int src = my_nbr[p * RSTEP * KOFF + koff];
+        const bool pr = kvalid && src >= 0;
+        ldg8_pred(a.in + (size_t)(pr ? src : 0) * CIN + coff, pr, da[p], db[p]);
       }
     };
-    if (nlist > 0) issue(s_list[0], v, pres);
+    if (nlist > 0) issue(s_list[0], va, vb);
     for (int i = 0; i < nlist; ++i) {
       const int s = i % kStages;
       const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-      float4 vn[F];
-      uint32_t pres_n = 0u;
-      if (i + 1 < nlist) issue(s_list[i + 1], vn, pres_n);     // loads of the next chunk fly while this one is converted
+      float4 na[F], nb[F];
+      if (i + 1 < nlist) issue(s_list[i + 1], na, nb);     // loads of the next chunk fly while this one is converted
       mbar_wait(&empty[s], ph ^ 1u);
-      uint8_t *a_hi = tiles + s * C::kStageBytes, *a_lo = a_hi + kABytes;
+      uint8_t *a_hi = tiles + s * C::kStageBytes + sw_off, *a_lo = a_hi + kABytes;
 #pragma unroll
       for (int p = 0; p < F; ++p) {
-        const int r = p * RSTEP + rsub;
-        uint2 hi = make_uint2(0u, 0u), lo = make_uint2(0u, 0u);
-        if ((pres >> p) & 1u) {
-          split2(v[p].x, v[p].y, hi.x, lo.x);
-          split2(v[p].z, v[p].w, hi.y, lo.y);
-        }
-        const int off = r * 128 + (((cidx >> 1) ^ (r & 7)) << 4) + ((cidx & 1) << 3);
-        *(uint2 *)(a_hi + off) = hi;
-        *(uint2 *)(a_lo + off) = lo;
+        uint4 hi, lo;
+        split2(va[p].x, va[p].y, hi.x, lo.x);
+        split2(va[p].z, va[p].w, hi.y, lo.y);
+        split2(vb[p].x, vb[p].y, hi.z, lo.z);
+        split2(vb[p].z, vb[p].w, hi.w, lo.w);
+        *(uint4 *)(a_hi + p * RSTEP * 128) = hi;
+        *(uint4 *)(a_lo + p * RSTEP * 128) = lo;
       }
       fence_proxy_async();
       mbar_arrive(&full[s]);
 #pragma unroll
-      for (int p = 0; p < F; ++p) v[p] = vn[p];
-      pres = pres_n;
+      for (int p = 0; p < F; ++p) { va[p] = na[p]; vb[p] = nb[p]; }
     }
     // ===================== epilogue: TMEM -> scale/shift/relu -> global =====================
     // warp w reads TMEM lane quarter (w & 3) and the column group (w >> 2)
@@ -291,18 +316,17 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
       if (row < a.n_out) {
         float *o = a.out + (size_t)row * COUT + c0;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int gg = 0; gg < 4; ++gg) {
           float4 y;
           float *yy = (float *)&y;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int c = c0 + g * 4 + e;
-            float val = __uint_as_float(r[g * 4 + e]);
-            val = val * (a.scale ? __ldg(a.scale + c) : 1.f) + (a.shift ? __ldg(a.shift + c) : 0.f);
+            const int c = c0 + gg * 4 + e;
+            float val = fmaf(__uint_as_float(r[gg * 4 + e]), s_scale[c], s_shift[c]);
             if (a.relu) val = fmaxf(val, 0.f);
             yy[e] = val;
           }
-          *(float4 *)(o + g * 4) = y;
+          *(float4 *)(o + gg * 4) = y;
         }
       }
     }
