@@ -205,7 +205,7 @@ int egn_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, 
                 const float *scale, const float *shift, int relu, float *out, egn_stream_t stream) {
   EGN_CHECK(ctx != nullptr && in && wpack && out, EGN_ERR_INVALID, "conv_tc: null argument");
   DeviceGuard g(ctx->device);
-  return run_conv_tc(ctx, level_in, ksize, transposed, cin, cout, in, wpack, scale, shift, relu, out, (cudaStream_t)stream);
+  return run_conv_tc(ctx, level_in, ksize, transposed, cin, cout, in, wpack, scale, shift, relu, 0, out, (cudaStream_t)stream);
 }
 
 int egn_set_tensor_cores(egn_ctx *ctx, int enable) {

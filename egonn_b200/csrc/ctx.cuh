@@ -31,6 +31,7 @@ struct HostCounts {  // pinned
   int n_batches;
   int status;
   int n_out;
+  int flags;   // [P+3] bit 0: some input feature != 1.0f (set by the forward's feature gather)
 };
 
 // per-kernel-class event timing (bench.py's live roofline numbers)
@@ -98,7 +99,7 @@ int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, in
 // sconv_tc.cu
 bool sconv_tc_supported(int ksize, int transposed, int cin, int cout);
 int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const void *wpack,
-                const float *scale, const float *shift, int relu, float *out, cudaStream_t s);
+                const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s);
 // forward.cu
 int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float *features, float *global_out,
             float *desc_out, float *kp_out, float *sigma_out, cudaStream_t s);

@@ -7,12 +7,12 @@ namespace egn {
 
 // ops.cu
 int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const float *scale, const float *shift, int cout,
-              int relu, float *out, cudaStream_t s);
+              int relu, const int *not_ones, float *out, cudaStream_t s);
 int run_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const float *w,
              const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s);
 int run_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, float p, float eps, float *part, int slices,
              float *out, cudaStream_t s);
-int run_gather_rows1(egn_ctx *ctx, const float *in, const int *perm, int n, float *out, cudaStream_t s);
+int run_gather_rows1(egn_ctx *ctx, const float *in, const int *perm, int n, float *out, int *not_ones, cudaStream_t s);
 int run_eca_gate(egn_ctx *ctx, int level, int c, const float *t, const float *wk, int k, float *part, int slices, float *gate,
                  cudaStream_t s);
 int run_eca_apply(egn_ctx *ctx, int level, int c, const float *t, const float *res, const float *gate, int relu, float *out,
@@ -34,8 +34,8 @@ struct Fwd {
 
   // conv described by an egn_layer on the pyramid
   int layer(const egn_layer &l, int level_in, int ksize, int transposed, const float *in, int relu, int accumulate, float *out) {
-    if (ctx->use_tc && l.wtc >= 0 && !accumulate && sconv_tc_supported(ksize, transposed, l.cin, l.cout))
-      return run_conv_tc(ctx, level_in, ksize, transposed, l.cin, l.cout, in, wb + l.wtc, W(l.scale), W(l.shift), relu, out, s);
+    if (ctx->use_tc && l.wtc >= 0 && sconv_tc_supported(ksize, transposed, l.cin, l.cout))
+      return run_conv_tc(ctx, level_in, ksize, transposed, l.cin, l.cout, in, wb + l.wtc, W(l.scale), W(l.shift), relu, accumulate, out, s);
     return run_conv(ctx, level_in, ksize, transposed, l.cin, l.cout, in, W(l.w), W(l.scale), W(l.shift), relu, accumulate, out, s);
   }
 };
@@ -111,9 +111,10 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
   float *f0 = F.alloc(py.n[0]);
   float *x0 = F.alloc((size_t)py.n[0] * net->conv0.cout);
   EGN_CHECK(f0 && x0, EGN_ERR_STATE, "feature arena exhausted (conv0)");
-  EGN_TRY(run_gather_rows1(ctx, features, py.perm0, py.n[0], f0, s));
+  int *not_ones = ctx->dev_counts + P + 3;
+  EGN_TRY(run_gather_rows1(ctx, features, py.perm0, py.n[0], f0, not_ones, s));
   EGN_TRY(run_conv0(ctx, net->conv0_ksize, f0, F.W(net->conv0.w), F.W(net->conv0.scale), F.W(net->conv0.shift),
-                    net->conv0.cout, 1, x0, s));
+                    net->conv0.cout, 1, not_ones, x0, s));
   tp.conv0 = x0;
   tp.c0 = net->conv0.cout;
 

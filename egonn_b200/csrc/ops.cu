@@ -192,8 +192,10 @@ __global__ void __launch_bounds__(kC0Warps * 32, 2) k_conv0(const float *__restr
                                                             const int *__restrict__ up1, const int *__restrict__ nbr2,
                                                             const uint64_t *__restrict__ mask64, const int *__restrict__ first0, int n0,
                                                             const float *__restrict__ w /* (KS^3,1,32) */, const float *__restrict__ scale,
-                                                            const float *__restrict__ shift, int relu, float *__restrict__ out) {
+                                                            const float *__restrict__ shift, int relu, const int *__restrict__ not_ones,
+                                                            float *__restrict__ out) {
   constexpr int KV = KS * KS * KS, R = KS / 2, COUT = 32;
+  const bool all_ones = not_ones != nullptr && *not_ones == 0;   // every input feature == 1.0f (what every EgoNN caller feeds)
   extern __shared__ __align__(16) uint8_t s_raw[];
   float *s_w = (float *)s_raw;                                           // [KV][36]
   unsigned long long *s_box = (unsigned long long *)(s_w + KV * kC0WStride + 4);   // [axis 3][l 4][delta 3]
@@ -224,33 +226,36 @@ __global__ void __launch_bounds__(kC0Warps * 32, 2) k_conv0(const float *__restr
       const int lx = (m & 1) | ((m >> 2) & 2), ly = ((m >> 1) & 1) | ((m >> 3) & 2), lz = ((m >> 2) & 1) | ((m >> 4) & 2);
       const int cell = up1[up0[r]];
       const int *nb = nbr2 + (int64_t)cell * 27;
-#pragma unroll 1
-      for (int dz = -1; dz <= 1; ++dz) {
-        const unsigned long long bz = s_box[24 + lz * 3 + dz + 1];
-        if (!bz) continue;
-#pragma unroll 1
-        for (int dy = -1; dy <= 1; ++dy) {
-          const unsigned long long byz = bz & s_box[12 + ly * 3 + dy + 1];
-          if (!byz) continue;
-#pragma unroll 1
-          for (int dx = -1; dx <= 1; ++dx) {
-            const unsigned long long box = byz & s_box[lx * 3 + dx + 1];
-            if (!box) continue;
-            const int q = nb[(dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)];
-            if (q < 0) continue;
-            const unsigned long long occ = mask64[q];
-            unsigned long long pm = occ & box;
-            const int fb = first0[q];
-            while (pm) {
-              const int b = __ffsll((long long)pm) - 1;
-              pm &= pm - 1;
-              const int x = (b & 1) | ((b >> 2) & 2), y = ((b >> 1) & 1) | ((b >> 3) & 2), z = ((b >> 2) & 1) | ((b >> 4) & 2);
-              const int t = (x + 4 * dx - lx + R) + KS * ((y + 4 * dy - ly + R) + KS * (z + 4 * dz - lz + R));
-              const int frow = fb + __popcll(occ & ((1ull << b) - 1ull));
-              list[cnt * 32 + lane] = (uint32_t)t | ((uint32_t)frow << 7);
-              ++cnt;
-            }
-          }
+      // the window touches at most two cells per axis: delta d0 = floor((l-R)/4) and d1 = floor((l+R)/4)
+      const int dx0 = (lx - R) >> 2, dx1 = (lx + R) >> 2, dy0 = (ly - R) >> 2, dy1 = (ly + R) >> 2, dz0 = (lz - R) >> 2,
+                dz1 = (lz + R) >> 2;
+      int q[8];
+      unsigned long long box[8], occ[8];
+      int fb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {          // 8 independent loads, then 16 more: two latencies instead of 24
+        const int dx = (i & 1) ? dx1 : dx0, dy = (i & 2) ? dy1 : dy0, dz = (i & 4) ? dz1 : dz0;
+        const bool dup = ((i & 1) && dx1 == dx0) || ((i & 2) && dy1 == dy0) || ((i & 4) && dz1 == dz0);
+        box[i] = dup ? 0ull : (s_box[lx * 3 + dx + 1] & s_box[12 + ly * 3 + dy + 1] & s_box[24 + lz * 3 + dz + 1]);
+        q[i] = box[i] ? nb[(dx + 1) + 3 * (dy + 1) + 9 * (dz + 1)] : -1;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        occ[i] = q[i] >= 0 ? mask64[q[i]] : 0ull;
+        fb[i] = q[i] >= 0 ? first0[q[i]] : 0;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int dx = (i & 1) ? dx1 : dx0, dy = (i & 2) ? dy1 : dy0, dz = (i & 4) ? dz1 : dz0;
+        unsigned long long pm = occ[i] & box[i];
+        while (pm) {
+          const int b = __ffsll((long long)pm) - 1;
+          pm &= pm - 1;
+          const int x = (b & 1) | ((b >> 2) & 2), y = ((b >> 1) & 1) | ((b >> 3) & 2), z = ((b >> 2) & 1) | ((b >> 4) & 2);
+          const int t = (x + 4 * dx - lx + R) + KS * ((y + 4 * dy - ly + R) + KS * (z + 4 * dz - lz + R));
+          const int frow = fb[i] + __popcll(occ[i] & ((1ull << b) - 1ull));
+          list[cnt * 32 + lane] = (uint32_t)t | ((uint32_t)frow << 7);
+          ++cnt;
         }
       }
     }
@@ -262,7 +267,7 @@ __global__ void __launch_bounds__(kC0Warps * 32, 2) k_conv0(const float *__restr
     for (int i = 0; i < maxcnt; ++i) {
       if (i < cnt) {
         const uint32_t e = list[i * 32 + lane];
-        const float f = f0[e >> 7];
+        const float f = all_ones ? 1.f : f0[e >> 7];
         const float4 *wr = (const float4 *)(s_w + (e & 127u) * kC0WStride);
 #pragma unroll
         for (int c4 = 0; c4 < COUT / 4; ++c4) {
@@ -297,8 +302,17 @@ __global__ void __launch_bounds__(kC0Warps * 32, 2) k_conv0(const float *__restr
 // ------------------------------------------------------------------------------------------------------
 // row-wise / per-cloud operators
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_gather_rows1(const float *__restrict__ in, const int *__restrict__ perm, int n, float *__restrict__ out) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = in[perm[i]];
+// canonical-order copy of the (n,1) input features; also records whether any feature differs from 1.0f
+__global__ void k_gather_rows1(const float *__restrict__ in, const int *__restrict__ perm, int n, float *__restrict__ out,
+                               int *__restrict__ not_ones) {
+  int bad = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float v = in[perm[i]];
+    out[i] = v;
+    bad |= (v != 1.0f);
+  }
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicOr(not_ones, 1);
 }
 
 // per-cloud column reduction, deterministic two-stage: block (b, s) reduces slice s of cloud b's rows.
@@ -480,7 +494,7 @@ __global__ void __launch_bounds__(256) k_topk_smallest(const float *__restrict__
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------
 int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const float *scale, const float *shift, int cout,
-              int relu, float *out, cudaStream_t s) {
+              int relu, const int *not_ones, float *out, cudaStream_t s) {
   const Pyramid &py = ctx->pyr;
   EGN_CHECK(ksize == 5 || ksize == 3, EGN_ERR_INVALID, "conv0: kernel size %d not supported (3 or 5)", ksize);
   EGN_CHECK(cout == 32, EGN_ERR_INVALID, "conv0: %d output channels not supported (the egonn / MinkLoc3D stems use 32)", cout);
@@ -496,11 +510,11 @@ int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const fl
     if (!attr) { EGN_CUDA(cudaFuncSetAttribute(k_conv0<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     EGN_LAUNCH(ctx, "conv0_5x5x5", bytes, flops, s,
                k_conv0<5><<<blocks, kC0Warps * 32, smem, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], py.mask64, py.first0, n0, w,
-                                                              scale, shift, relu, out));
+                                                              scale, shift, relu, not_ones, out));
   } else {
     EGN_LAUNCH(ctx, "conv0_3x3x3", bytes, flops, s,
                k_conv0<3><<<blocks, kC0Warps * 32, smem, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], py.mask64, py.first0, n0, w,
-                                                              scale, shift, relu, out));
+                                                              scale, shift, relu, not_ones, out));
   }
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
@@ -536,7 +550,7 @@ int run_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int
     pairs = a.n_out;
   } else if (ksize == 5) {
     EGN_CHECK(level_in == 0 && cin == 1 && !accumulate, EGN_ERR_INVALID, "conv k=5 is supported at level 0 with cin=1 only");
-    return run_conv0(ctx, 5, in, w, scale, shift, cout, relu, out, s);
+    return run_conv0(ctx, 5, in, w, scale, shift, cout, relu, nullptr, out, s);
   } else {
     EGN_CHECK(false, EGN_ERR_INVALID, "conv: unsupported kernel size %d", ksize);
   }
@@ -602,8 +616,10 @@ int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, in
 }
 
 // exported to forward.cu
-int run_gather_rows1(egn_ctx *ctx, const float *in, const int *perm, int n, float *out, cudaStream_t s) {
-  EGN_LAUNCH(ctx, "gather_input_features", (double)n * 12, 0, s, k_gather_rows1<<<grid_for(n, 256), 256, 0, s>>>(in, perm, n, out));
+int run_gather_rows1(egn_ctx *ctx, const float *in, const int *perm, int n, float *out, int *not_ones, cudaStream_t s) {
+  EGN_CUDA(cudaMemsetAsync(not_ones, 0, sizeof(int), s));
+  EGN_LAUNCH(ctx, "gather_input_features", (double)n * 12, 0, s,
+             k_gather_rows1<<<grid_for(n, 256), 256, 0, s>>>(in, perm, n, out, not_ones));
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
 }

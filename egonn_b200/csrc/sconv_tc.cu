@@ -138,7 +138,7 @@ struct Args {
   float *out;
   const uint8_t *wpack;  // [n_chunks][hi|lo][COUT][64] bf16, swizzled shared-memory images
   const float *scale, *shift;
-  int n_out, relu, mode;  // mode 1: 27-neighbour table, 2: 2x2x2 stride-2 children, 3: transposed 2x2x2 (parent, slice = own code)
+  int n_out, relu, accumulate, mode;  // mode 0: identity rows (1x1x1 convolution), 1: 27-neighbour table, 2: 2x2x2 stride-2 children, 3: transposed 2x2x2 (parent, slice = own code)
   const int *nbr;
   const int *cstart;
   const uint32_t *cmask;
@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
       const int r = t / KOFF, k = t - r * KOFF, row = row0 + r;
       src[it] = -1;
       if (t < kRows * KOFF && row < a.n_out) {
-        if (a.mode == 1) src[it] = __ldg(a.nbr + (int64_t)row0 * 27 + t);
+        if (a.mode == 0) src[it] = row;
+        else if (a.mode == 1) src[it] = __ldg(a.nbr + (int64_t)row0 * 27 + t);
         else if (a.mode == 2) {
           const uint32_t m = __ldg(a.cmask + row);
           if ((m >> k) & 1u) src[it] = __ldg(a.cstart + row) + __popc(m & ((1u << k) - 1u));
@@ -326,6 +327,10 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
             if (a.relu) val = fmaxf(val, 0.f);
             yy[e] = val;
           }
+          if (a.accumulate) {
+            const float4 prev = *(const float4 *)(o + gg * 4);
+            y.x += prev.x; y.y += prev.y; y.z += prev.z; y.w += prev.w;
+          }
           *(float4 *)(o + gg * 4) = y;
         }
       }
@@ -391,6 +396,8 @@ static int launch(egn_ctx *ctx, const Args &a, const char *name, double bytes, d
 }  // namespace tc
 
 bool sconv_tc_supported(int ksize, int transposed, int cin, int cout) {
+  if (ksize == 1) return !transposed && ((cin == 32 && cout == 64) || (cin == 64 && (cout == 64 || cout == 128)) ||
+                                         (cin == 128 && (cout == 64 || cout == 128)));
   if (transposed) return ksize == 2 && cin == cout && (cin == 32 || cin == 64 || cin == 128);
   if (ksize == 3) return (cin == 32 && (cout == 32 || cout == 64)) || (cin == 64 && (cout == 64 || cout == 128)) || (cin == 128 && cout == 128);
   if (ksize == 2) return cin == cout && (cin == 32 || cin == 64 || cin == 128);
@@ -399,22 +406,27 @@ bool sconv_tc_supported(int ksize, int transposed, int cin, int cout) {
 
 // packed-weight bytes for a (ksize, cin, cout) convolution: n_chunks * 2 images * cout * 128
 size_t sconv_tc_wpack_bytes(int ksize, int cin, int cout) {
-  const int koff = ksize == 3 ? 27 : 8;
+  const int koff = ksize == 3 ? 27 : (ksize == 2 ? 8 : 1);
   return (size_t)((koff * cin + 63) / 64) * 2 * cout * 128;
 }
 
 int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const void *wpack,
-                const float *scale, const float *shift, int relu, float *out, cudaStream_t s) {
+                const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s) {
   const Pyramid &py = ctx->pyr;
   EGN_CHECK(py.valid, EGN_ERR_STATE, "conv before coords_build");
   EGN_CHECK(sconv_tc_supported(ksize, transposed, cin, cout), EGN_ERR_INVALID, "tensor-core conv: unsupported shape k=%d %d->%d", ksize, cin, cout);
   EGN_CHECK(((uintptr_t)wpack & 15) == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, EGN_ERR_INVALID,
             "tensor-core conv: pointers must be 16-byte aligned");
   tc::Args a = {};
-  a.in = in; a.out = out; a.wpack = (const uint8_t *)wpack; a.scale = scale; a.shift = shift; a.relu = relu;
+  a.in = in; a.out = out; a.wpack = (const uint8_t *)wpack; a.scale = scale; a.shift = shift; a.relu = relu; a.accumulate = accumulate;
   long long pairs;
   char name[48];
-  if (ksize == 3) {
+  if (ksize == 1) {
+    EGN_CHECK(level_in >= 0 && level_in < P, EGN_ERR_INVALID, "conv k=1: bad level");
+    a.mode = 0; a.n_out = py.n[level_in];
+    pairs = a.n_out;
+    snprintf(name, sizeof(name), "tc_rowmm_c%d_%d", cin, cout);
+  } else if (ksize == 3) {
     EGN_CHECK(level_in >= 1 && level_in < P, EGN_ERR_INVALID, "conv k=3: bad level");
     a.mode = 1; a.n_out = py.n[level_in]; a.nbr = py.nbr[level_in];
     pairs = py.pairs27[level_in];
@@ -431,19 +443,25 @@ int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, 
     snprintf(name, sizeof(name), "tc_conv2x2x2s2_c%d_%d", cin, cout);
   }
   if (a.n_out == 0) return EGN_OK;
-  const int K = ksize == 3 ? 27 : 8;
-  const double bytes = (double)pairs * (cin + cout) * 4 + (double)pairs * 8 + (double)K * cin * cout * 4;
+  const int K = ksize == 3 ? 27 : (ksize == 2 ? 8 : 1);
+  const double bytes = ksize == 1 ? (double)pairs * (cin + cout) * 4
+                                  : (double)pairs * (cin + cout) * 4 + (double)pairs * 8 + (double)K * cin * cout * 4;
   const double flops = 2.0 * pairs * cin * cout;
-#define EGN_TC_CASE(CI, CO)                                                                         \
-  if (cin == CI && cout == CO) {                                                                    \
-    if (ksize == 3) return tc::launch<CI, CO, 27>(ctx, a, name, bytes, flops, s);                   \
-    return tc::launch<CI, CO, 8>(ctx, a, name, bytes, flops, s);                                    \
-  }
-  EGN_TC_CASE(32, 32)
-  EGN_TC_CASE(32, 64)
-  EGN_TC_CASE(64, 64)
-  EGN_TC_CASE(64, 128)
-  EGN_TC_CASE(128, 128)
+#define EGN_TC_CASE(KS, KO, CI, CO) \
+  if (ksize == KS && cin == CI && cout == CO) return tc::launch<CI, CO, KO>(ctx, a, name, bytes, flops, s);
+  EGN_TC_CASE(3, 27, 32, 32)
+  EGN_TC_CASE(3, 27, 32, 64)
+  EGN_TC_CASE(3, 27, 64, 64)
+  EGN_TC_CASE(3, 27, 64, 128)
+  EGN_TC_CASE(3, 27, 128, 128)
+  EGN_TC_CASE(2, 8, 32, 32)
+  EGN_TC_CASE(2, 8, 64, 64)
+  EGN_TC_CASE(2, 8, 128, 128)
+  EGN_TC_CASE(1, 1, 32, 64)
+  EGN_TC_CASE(1, 1, 64, 64)
+  EGN_TC_CASE(1, 1, 64, 128)
+  EGN_TC_CASE(1, 1, 128, 64)
+  EGN_TC_CASE(1, 1, 128, 128)
 #undef EGN_TC_CASE
   EGN_CHECK(false, EGN_ERR_INVALID, "tensor-core conv: no kernel instance");
 }

@@ -37,7 +37,8 @@ def _bn_fold(sd, prefix, eps=1e-5):
     return scale, b - m * scale
 
 
-TC_SHAPES = {27: {(32, 32), (32, 64), (64, 64), (64, 128), (128, 128)}, 8: {(32, 32), (64, 64), (128, 128)}}
+TC_SHAPES = {27: {(32, 32), (32, 64), (64, 64), (64, 128), (128, 128)}, 8: {(32, 32), (64, 64), (128, 128)},
+             1: {(32, 64), (64, 64), (64, 128), (128, 64), (128, 128)}}
 
 
 def pack_tc(kernel: torch.Tensor) -> torch.Tensor:

@@ -163,7 +163,8 @@ int egn_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int
              const float *in, const float *w, const float *scale, const float *shift, int relu,
              int accumulate, float *out, egn_stream_t stream);
 /* Tensor-core (tcgen05) variant of egn_conv for ksize 3 (cin->cout in {32->32, 32->64, 64->64, 64->128, 128->128})
- * and ksize 2 stride 2, plain or transposed (cin == cout in {32, 64, 128}).  wpack is the kernel pre-split into bf16 hi/lo and laid out
+ * ksize 2 stride 2, plain or transposed (cin == cout in {32, 64, 128}) and ksize 1 ({32->64, 64->64, 64->128,
+ * 128->64, 128->128}).  wpack is the kernel pre-split into bf16 hi/lo and laid out
  * as the 128-byte-swizzled shared-memory images the kernel loads with one bulk copy per 64-element reduction chunk:
  * [ceil(K*cin/64)][hi|lo][cout][64] bf16 with 16-byte group g of row n stored at group g ^ (n & 7)
  * (egonn_b200/weights.py:pack_tc).  Results are fp32-class (bf16x3 split products, FP32 accumulation in TMEM). */

@@ -301,3 +301,16 @@ def test_tensor_core_transposed_conv(c, cuda):
         y_f32 = eng.conv(level, 2, True, x, w)
         assert y_tc.shape == (info.n_rows[level - 1], c)
         assert_close_rel(y_tc, y_f32, 2e-5, f"tconv level {level}")
+
+
+@pytest.mark.parametrize("cin,cout", [(32, 64), (64, 64), (64, 128), (128, 64), (128, 128)])
+def test_tensor_core_1x1_conv(cin, cout, cuda):
+    import egonn_b200 as E
+    g = load_golden("mini3_cartesian")
+    eng = E.Engine(cuda)
+    info = eng.build(torch.from_numpy(g["coords"]).to(cuda))
+    torch.manual_seed(cin + cout)
+    x = torch.randn(info.n_rows[2], cin, device=cuda)
+    w = torch.randn(1, cin, cout, device=cuda) / np.sqrt(cin)
+    y = eng.conv_tc(2, 1, x, w)
+    assert_close_rel(y, x @ w[0], 2e-5, f"1x1 {cin}->{cout}")
