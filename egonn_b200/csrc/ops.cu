@@ -446,48 +446,102 @@ __global__ void k_kp_sigma(const float *__restrict__ kp_raw /* (n,3) */, const f
   }
 }
 
-// per-cloud k smallest sigma (eval/evaluate.py:352-361): one CTA per cloud, k rounds of block arg-min over the
-// elements lexicographically greater than the previous pick (value, then row) - stable, no marking needed.
-__global__ void __launch_bounds__(256) k_topk_smallest(const float *__restrict__ sigma, const int *__restrict__ off, int k,
-                                                       int smem_cap, int *__restrict__ idx_out) {
-  extern __shared__ float s_val[];
-  __shared__ float s_bv[8];
-  __shared__ int s_bi[8];
-  __shared__ float s_pv;
-  __shared__ int s_pi;
-  const int b = blockIdx.x, r0 = off[b], len = off[b + 1] - r0;
-  const bool in_smem = len <= smem_cap;
-  if (in_smem)
-    for (int i = threadIdx.x; i < len; i += blockDim.x) s_val[i] = sigma[r0 + i];
-  if (threadIdx.x == 0) { s_pv = -INFINITY; s_pi = -1; }
+// per-cloud k smallest sigma (eval/evaluate.py:352-361: torch.topk(sigma, k, largest=False), sorted ascending).
+// One CTA per cloud: 4-pass MSB radix select (8-bit digits, shared-memory histograms) finds the k-th smallest key,
+// everything below it is collected, ties on the threshold are taken in row order, and the <= 256 survivors are
+// bitonic-sorted by (value, row).  O(n) per cloud instead of k passes over the data.
+constexpr int kTopkThreads = 1024;
+constexpr int kTopkMaxK = 1024;
+
+__device__ __forceinline__ uint32_t float_order_key(float v) {   // monotone float -> uint32 (NaN sorts last)
+  const uint32_t u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__global__ void __launch_bounds__(kTopkThreads) k_topk_smallest(const float *__restrict__ sigma, const int *__restrict__ off, int k,
+                                                                int *__restrict__ idx_out) {
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned long long s_cand[kTopkMaxK];
+  __shared__ unsigned int s_prefix, s_remaining, s_ncand, s_tie_base;
+  __shared__ unsigned int s_warp[32];
+  const int b = blockIdx.x, r0 = off[b], n = off[b + 1] - r0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int kk = min(k, n);
+  int *out = idx_out + (size_t)b * k;
+  if (kk == 0) {
+    for (int i = tid; i < k; i += kTopkThreads) out[i] = -1;
+    return;
+  }
+  if (tid == 0) { s_prefix = 0u; s_remaining = (unsigned)kk; s_ncand = 0u; s_tie_base = 0u; }
   __syncthreads();
-  for (int j = 0; j < k; ++j) {
-    const float pv = s_pv;
-    const int pi = s_pi;
-    float bv = INFINITY;
-    int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < len; i += blockDim.x) {
-      const float v = in_smem ? s_val[i] : sigma[r0 + i];
-      const bool after = v > pv || (v == pv && i > pi);
-      if (after && (v < bv || (v == bv && i < bi))) { bv = v; bi = i; }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-      if (oi != 0x7fffffff && (bi == 0x7fffffff || ov < bv || (ov == bv && oi < bi))) { bv = ov; bi = oi; }
-    }
-    if ((threadIdx.x & 31) == 0) { s_bv[threadIdx.x >> 5] = bv; s_bi[threadIdx.x >> 5] = bi; }
+  // ---- radix select: after pass p the top 8*(p+1) bits of the k-th smallest key are known ----
+  for (int pass = 0; pass < 4; ++pass) {
+    const int shift = 24 - 8 * pass;
+    for (int i = tid; i < 256; i += kTopkThreads) s_hist[i] = 0u;
     __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < 8; ++w)
-        if (s_bi[w] != 0x7fffffff && (bi == 0x7fffffff || s_bv[w] < bv || (s_bv[w] == bv && s_bi[w] < bi))) { bv = s_bv[w]; bi = s_bi[w]; }
-      const bool ok = bi != 0x7fffffff;
-      idx_out[(size_t)b * k + j] = ok ? bi : -1;
-      if (ok) { s_pv = bv; s_pi = bi; } else { s_pv = INFINITY; s_pi = 0x7fffffff; }
+    const unsigned int prefix = s_prefix;
+    const unsigned int himask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+    for (int i = tid; i < n; i += kTopkThreads) {
+      const uint32_t key = float_order_key(sigma[r0 + i]);
+      if ((key & himask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {                                      // find the digit holding the `remaining`-th element
+      unsigned int c[8], sum = 0u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { c[j] = s_hist[lane * 8 + j]; sum += c[j]; }
+      unsigned int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      unsigned int before = incl - sum;
+      const unsigned int rem = s_remaining;
+      if (before < rem && rem <= incl) {                  // exactly one lane
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (rem <= before + c[j]) { s_prefix = prefix | ((unsigned)(lane * 8 + j) << shift); s_remaining = rem - before; break; }
+          before += c[j];
+        }
+      }
     }
     __syncthreads();
   }
+  const unsigned int T = s_prefix;           // key of the k-th smallest element
+  const unsigned int need_ties = s_remaining; // how many elements equal to T belong to the result (lowest rows first)
+  // ---- collect: keys < T unordered, keys == T in row order ----
+  for (int base = 0; base < n; base += kTopkThreads) {
+    const int i = base + tid;
+    uint32_t key = 0xFFFFFFFFu;
+    bool lt = false, eq = false;
+    if (i < n) { key = float_order_key(sigma[r0 + i]); lt = key < T; eq = key == T; }
+    if (lt) s_cand[atomicAdd(&s_ncand, 1u)] = ((unsigned long long)key << 32) | (unsigned)i;
+    const unsigned int bal = __ballot_sync(0xffffffffu, eq);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    unsigned int wbase = s_tie_base;
+    for (int w = 0; w < warp; ++w) wbase += s_warp[w];
+    const unsigned int rank = wbase + __popc(bal & ((1u << lane) - 1u));
+    if (eq && rank < need_ties) s_cand[atomicAdd(&s_ncand, 1u)] = ((unsigned long long)key << 32) | (unsigned)i;
+    __syncthreads();
+    if (tid == 0) { unsigned int t = 0; for (int w = 0; w < 32; ++w) t += s_warp[w]; s_tie_base += t; }
+    __syncthreads();
+  }
+  // ---- bitonic sort of the kk survivors by (key, row) ----
+  int m = 1;
+  while (m < kk) m <<= 1;
+  for (int i = kk + tid; i < m; i += kTopkThreads) s_cand[i] = ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= m; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < m / 2; t += kTopkThreads) {
+        const int lo = (t / stride) * stride * 2 + (t % stride), hi = lo + stride;
+        const bool up = ((lo & size) == 0);
+        const unsigned long long x = s_cand[lo], y = s_cand[hi];
+        if ((x > y) == up) { s_cand[lo] = y; s_cand[hi] = x; }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < k; i += kTopkThreads) out[i] = i < kk ? (int)(unsigned)(s_cand[i] & 0xFFFFFFFFull) : -1;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -608,9 +662,8 @@ int op_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const floa
 
 int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out, cudaStream_t s) {
   EGN_CHECK(sigma && offsets && idx_out && n_batches >= 1 && k >= 1, EGN_ERR_INVALID, "topk: bad argument");
-  // clouds up to 8k rows are staged in shared memory, larger ones are re-read from L2
-  const int cap = 8 * 1024;
-  k_topk_smallest<<<n_batches, 256, (size_t)cap * 4, s>>>(sigma, offsets, k, cap, idx_out);
+  EGN_CHECK(k <= kTopkMaxK, EGN_ERR_INVALID, "topk: k=%d exceeds %d", k, kTopkMaxK);
+  k_topk_smallest<<<n_batches, kTopkThreads, 0, s>>>(sigma, offsets, k, idx_out);
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
 }

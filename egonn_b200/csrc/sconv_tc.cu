@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], PT + 1);    // every gather thread + the TMA thread's arrive.expect_tx
+      mbar_init(&full[s], NPW + 1);   // one arrive per gather warp + the TMA thread's arrive.expect_tx
       mbar_init(&empty[s], 1);        // one tcgen05.commit
     }
     mbar_init(accum, 1);
@@ -297,8 +297,9 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
         *(uint4 *)(a_hi + p * RSTEP * 128) = hi;
         *(uint4 *)(a_lo + p * RSTEP * 128) = lo;
       }
-      fence_proxy_async();
-      mbar_arrive(&full[s]);
+      fence_proxy_async();            // this thread's generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();                   // ... of all 32 lanes, then ONE mbarrier arrive per warp instead of 32
+      if (lane == 0) mbar_arrive(&full[s]);
 #pragma unroll
       for (int p = 0; p < F; ++p) { va[p] = na[p]; vb[p] = nb[p]; }
     }

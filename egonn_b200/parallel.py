@@ -1,0 +1,68 @@
+"""Data-parallel descriptor extraction over point clouds.
+
+The reference is single-process / single-device (eval/evaluate.py:454-466); each cloud's forward is independent
+of every other (eval-mode BatchNorm is affine; ECA and GeM reduce per cloud: layers/eca_block.py:23,
+layers/pooling.py:84-86), so the path shards over clouds with NO collective inside the network.  One process
+per GPU; the only exchange is one all-gather of the (B_local, 256) global descriptors (NCCL over NVLink on the
+B200 box, gloo in the CPU tests).  Local descriptors / keypoints stay on the rank that produced them.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_clouds(sizes: Sequence[int], world_size: int) -> List[List[int]]:
+    """Greedy balance: clouds sorted by voxel (or point) count, each to the currently lightest rank.
+    Returns, per rank, the ORIGINAL indices of its clouds in ascending order; deterministic on every rank."""
+    order = sorted(range(len(sizes)), key=lambda i: (-int(sizes[i]), i))
+    load = [0] * world_size
+    parts: List[List[int]] = [[] for _ in range(world_size)]
+    for i in order:
+        r = min(range(world_size), key=lambda k: (load[k], k))
+        parts[r].append(i)
+        load[r] += int(sizes[i])
+    return [sorted(p) for p in parts]
+
+
+def gather_global(local: torch.Tensor, parts: List[List[int]], group=None) -> torch.Tensor:
+    """All-gather the per-rank (B_r, D) global descriptors and restore the original cloud order: (B, D).
+    Ranks may own different numbers of clouds: rows are padded to the largest share for the collective."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    total = sum(len(p) for p in parts)
+    if world == 1:
+        out = torch.empty((total, local.shape[1]), dtype=local.dtype, device=local.device)
+        out[torch.tensor(parts[0], device=local.device, dtype=torch.long)] = local
+        return out
+    bmax = max(len(p) for p in parts)
+    pad = torch.zeros((bmax, local.shape[1]), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    buf = torch.empty((world * bmax, local.shape[1]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(buf, pad, group=group)
+    out = torch.empty((total, local.shape[1]), dtype=local.dtype, device=local.device)
+    for r, p in enumerate(parts):
+        if p:
+            out[torch.tensor(p, device=local.device, dtype=torch.long)] = buf[r * bmax: r * bmax + len(p)]
+    return out
+
+
+def extract_sharded(model, clouds_coords: List[torch.Tensor], batched_coordinates, group=None) -> Tuple[torch.Tensor, Dict]:
+    """Run ``model.forward_packed`` on this rank's share of ``clouds_coords`` (list of (Mi,3) int32 voxel coords on
+    the rank's device) and return (all global descriptors (B,256) in original order, this rank's packed local outputs
+    with ``cloud_ids`` = original indices of its clouds)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    parts = shard_clouds([int(c.shape[0]) for c in clouds_coords], world)
+    mine = parts[rank]
+    dev = clouds_coords[0].device
+    if mine:
+        bc = batched_coordinates([clouds_coords[i] for i in mine])
+        feats = torch.ones((bc.shape[0], 1), device=dev)
+        local = model.forward_packed({"coords": bc, "features": feats})
+        g = local["global"]
+    else:
+        local, g = {}, torch.zeros((0, model.global_descriptor_size), device=dev)
+    local["cloud_ids"] = mine
+    return gather_global(g, parts, group), local

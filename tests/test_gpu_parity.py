@@ -220,17 +220,20 @@ def test_batch_independence_and_heads_switches(cuda, weights):
 def test_topk_smallest_matches_torch(cuda):
     import egonn_b200 as E
     torch.manual_seed(0)
-    lens = [300, 5, 0, 1000]
+    lens = [300, 5, 0, 1000, 20000, 256, 257]
     off = torch.tensor(np.cumsum([0] + lens), dtype=torch.int32, device=cuda)
     s = torch.rand(sum(lens), device=cuda)
     s[10] = s[20]                                                   # a tie: lower row first
-    idx = E.topk_smallest(s, off, 128).cpu()
-    for b, n in enumerate(lens):
-        k = min(n, 128)
-        seg = s[off[b]:off[b + 1]].cpu()
-        exp = torch.sort(seg, stable=True).indices[:k]
-        assert torch.equal(idx[b, :k].long(), exp)
-        assert torch.all(idx[b, k:] == -1)
+    s[1305 + 100: 1305 + 700] = 0.25                                # 600 equal values straddling the threshold of cloud 4
+    s[1305:1305 + 50] = -1.0                                        # negatives sort first
+    for k in (128, 256):
+        idx = E.topk_smallest(s, off, k).cpu()
+        for b, n in enumerate(lens):
+            kk = min(n, k)
+            seg = s[off[b]:off[b + 1]].cpu()
+            exp = torch.sort(seg, stable=True).indices[:kk]
+            assert torch.equal(idx[b, :kk].long(), exp), (k, b)
+            assert torch.all(idx[b, kk:] == -1)
 
 
 # ---------------------------------------------------------------------------------------------------------------
