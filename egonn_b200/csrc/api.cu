@@ -150,6 +150,13 @@ int egn_coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n, egn_coords_
   return coords_build(ctx, coords, n, info, (cudaStream_t)stream);
 }
 
+int egn_coords_build_points(egn_ctx *ctx, const float *points, int64_t n, const int32_t *cloud_offsets, int n_clouds,
+                            const float step[3], int polar, egn_coords_info *info, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return coords_build_points(ctx, points, n, cloud_offsets, n_clouds, step, polar, info, (cudaStream_t)stream);
+}
+
 int egn_coords_get(egn_ctx *ctx, int level, int32_t *out, egn_stream_t stream) {
   EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
   DeviceGuard g(ctx->device);

@@ -331,10 +331,42 @@ static size_t sort_scratch_bytes(int64_t n) {
   return pad256(n * 8) * 2 + pad256(n * 4) * 2 + pad256(sort_temp_bytes((int)n, 64)) + pad256(nblocks * P * 4) + (1 << 16);
 }
 
+__global__ void k_quant_pack_batch(const float *__restrict__ pts, int n, const int *__restrict__ cloud_off, int n_clouds, float q0,
+                                   float q1, float q2, int polar, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                   int *__restrict__ dev_counts);
+
+struct BuildSource {
+  const int32_t *coords = nullptr;   // (n,4) voxel coordinates, or
+  const float *points = nullptr;     // (n,3) raw points of n_clouds concatenated clouds
+  const int *cloud_off = nullptr;
+  int n_clouds = 0;
+  float step[3] = {1.f, 1.f, 1.f};
+  int polar = 0;
+};
+
+static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64, egn_coords_info *info, cudaStream_t s);
+
 int coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n64, egn_coords_info *info, cudaStream_t s) {
   EGN_CHECK(ctx && coords && info, EGN_ERR_INVALID, "coords_build: null argument");
-  EGN_CHECK(n64 > 0 && n64 < (int64_t)1 << 26, EGN_ERR_INVALID, "coords_build: n=%lld out of range (1..2^26)", (long long)n64);
   EGN_CHECK(((uintptr_t)coords & 15) == 0, EGN_ERR_INVALID, "coords_build: coords must be 16-byte aligned");
+  BuildSource src;
+  src.coords = coords;
+  return coords_build_common(ctx, src, n64, info, s);
+}
+
+int coords_build_points(egn_ctx *ctx, const float *points, int64_t n64, const int32_t *cloud_offsets, int n_clouds,
+                        const float step[3], int polar, egn_coords_info *info, cudaStream_t s) {
+  EGN_CHECK(ctx && points && cloud_offsets && step && info, EGN_ERR_INVALID, "coords_build_points: null argument");
+  EGN_CHECK(n_clouds >= 1 && n_clouds < kMaxBatch, EGN_ERR_RANGE, "coords_build_points: %d clouds (1..%d)", n_clouds, kMaxBatch - 1);
+  EGN_CHECK(step[0] > 0.f && (!polar || (step[1] > 0.f && step[2] > 0.f)), EGN_ERR_INVALID, "coords_build_points: step must be > 0");
+  BuildSource src;
+  src.points = points; src.cloud_off = cloud_offsets; src.n_clouds = n_clouds; src.polar = polar;
+  src.step[0] = step[0]; src.step[1] = step[1]; src.step[2] = step[2];
+  return coords_build_common(ctx, src, n64, info, s);
+}
+
+static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64, egn_coords_info *info, cudaStream_t s) {
+  EGN_CHECK(n64 > 0 && n64 < (int64_t)1 << 26, EGN_ERR_INVALID, "coords_build: n=%lld out of range (1..2^26)", (long long)n64);
   const int n = (int)n64;
   Pyramid &py = ctx->pyr;
   py = Pyramid();
@@ -348,8 +380,13 @@ int coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n64, egn_coords_in
   EGN_CHECK(kin && kout && vin && vout && counts, EGN_ERR_STATE, "scratch arena exhausted");
 
   EGN_CUDA(cudaMemsetAsync(ctx->dev_counts, 0, sizeof(HostCounts), s));
-  EGN_LAUNCH(ctx, "coords_pack_keys", (double)n * 28, 0, s,
-             k_pack_keys<<<grid_for(n, 256), 256, 0, s>>>((const int4 *)coords, n, kin, vin, ctx->dev_counts));
+  if (src.coords)
+    EGN_LAUNCH(ctx, "coords_pack_keys", (double)n * 28, 0, s,
+               k_pack_keys<<<grid_for(n, 256), 256, 0, s>>>((const int4 *)src.coords, n, kin, vin, ctx->dev_counts));
+  else
+    EGN_LAUNCH(ctx, "quantize_pack_batch", (double)n * 24, 0, s,
+               k_quant_pack_batch<<<grid_for(n, 256), 256, 0, s>>>(src.points, n, src.cloud_off, src.n_clouds, src.step[0], src.step[1],
+                                                                  src.step[2], src.polar, kin, vin, ctx->dev_counts));
   if (ctx->prof.on) ctx->prof.begin("coords_radix_sort(cub)", (double)n * 24 * 8, 0, s);
   EGN_TRY(sort_pairs(sc, kin, kout, vin, vout, n, 64, s));
   if (ctx->prof.on) ctx->prof.end(s);
@@ -364,7 +401,7 @@ int coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n64, egn_coords_in
   info->status = hc.status ? EGN_ERR_RANGE : EGN_OK;
   for (int L = 0; L < P; ++L) info->n_rows[L] = hc.totals[L];
   EGN_CHECK(hc.status == 0, EGN_ERR_RANGE,
-            "coords_build: coordinate outside [-2^17, 2^17) or batch index outside [0, 1023)");
+            "coords_build: coordinate outside [-2^17, 2^17) (or NaN point) or batch index outside [0, 1023)");
 
   // exact-size pyramid storage
   const int B = hc.n_batches;
@@ -487,6 +524,42 @@ __global__ void k_quant_pack(const float *__restrict__ pts, int n, float q0, flo
   }
   bad = __reduce_max_sync(0xffffffffu, bad);
   if ((threadIdx.x & 31) == 0 && bad) atomicOr(&dev_counts[P + 1], 1);
+}
+
+// fused path: raw points of B concatenated clouds -> level-0 keys (batch | Morton(voxel)) in one pass; the cloud of a
+// point comes from a binary search in the (B+1) point offsets.  Same arithmetic as k_quant_pack.
+__global__ void k_quant_pack_batch(const float *__restrict__ pts, int n, const int *__restrict__ cloud_off, int n_clouds, float q0,
+                                   float q1, float q2, int polar, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                   int *__restrict__ dev_counts) {
+  int bad = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int lo = 0, hi = n_clouds;                       // last cloud c with cloud_off[c] <= i
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (__ldg(cloud_off + mid) <= i) lo = mid; else hi = mid;
+    }
+    float x = pts[3 * (size_t)i], y = pts[3 * (size_t)i + 1], z = pts[3 * (size_t)i + 2];
+    float a, b, c;
+    if (polar) {
+      const float theta = __fadd_rn(180.f, __fdiv_rn(__fmul_rn(atan2f(y, x), 180.f), 3.14159265358979323846f));
+      const float dist = sqrtf(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)));
+      a = __fdiv_rn(theta, q0); b = __fdiv_rn(dist, q1); c = __fdiv_rn(z, q2);
+    } else if (q0 != 1.0f) {
+      a = __fdiv_rn(x, q0); b = __fdiv_rn(y, q0); c = __fdiv_rn(z, q0);
+    } else {
+      a = x; b = y; c = z;
+    }
+    const float fa = floorf(a), fb = floorf(b), fc = floorf(c);
+    const float lim = (float)kAxisBias;
+    const bool ok = fa >= -lim && fa < lim && fb >= -lim && fb < lim && fc >= -lim && fc < lim;
+    int ia = 0, ib = 0, ic = 0;
+    if (ok) { ia = (int)fa; ib = (int)fb; ic = (int)fc; } else bad = 1;
+    keys[i] = make_key(0, (uint32_t)lo, (uint32_t)(ia + kAxisBias), (uint32_t)(ib + kAxisBias), (uint32_t)(ic + kAxisBias));
+    vals[i] = (uint32_t)i;
+  }
+  bad = __reduce_max_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicOr(&dev_counts[P + 1], 1);
+  if (blockIdx.x == 0 && threadIdx.x == 0) dev_counts[P] = n_clouds;
 }
 
 // stable sort => the first element of every run of equal keys is the earliest input row

@@ -86,6 +86,8 @@ struct egn_ctx {
 namespace egn {
 // coords.cu
 int coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n, egn_coords_info *info, cudaStream_t s);
+int coords_build_points(egn_ctx *ctx, const float *points, int64_t n, const int32_t *cloud_offsets, int n_clouds,
+                        const float step[3], int polar, egn_coords_info *info, cudaStream_t s);
 int coords_get(egn_ctx *ctx, int level, int32_t *out, cudaStream_t s);
 int quantize(egn_ctx *ctx, const float *points, int64_t n, const float step[3], int polar, int32_t *coords_out,
              int64_t *index_out, int64_t *n_out, cudaStream_t s);

@@ -92,7 +92,7 @@ int run_head(Fwd &F, const egn_head &h, float *const x[], float **out_map) {
 
 int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float *features, float *global_out,
             float *desc_out, float *kp_out, float *sigma_out, cudaStream_t s) {
-  EGN_CHECK(ctx && net && weights && features, EGN_ERR_INVALID, "forward: null argument");
+  EGN_CHECK(ctx && net && weights, EGN_ERR_INVALID, "forward: null argument");
   Pyramid &py = ctx->pyr;
   EGN_CHECK(py.valid, EGN_ERR_STATE, "forward before coords_build");
   EGN_CHECK(net->n_levels >= 1 && net->n_levels < EGN_MAX_LEVELS && net->n_levels + 2 < P, EGN_ERR_INVALID, "forward: n_levels out of range");

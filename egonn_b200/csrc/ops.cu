@@ -669,8 +669,16 @@ int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, in
 }
 
 // exported to forward.cu
+__global__ void k_fill_ones(float *__restrict__ out, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = 1.0f;
+}
 int run_gather_rows1(egn_ctx *ctx, const float *in, const int *perm, int n, float *out, int *not_ones, cudaStream_t s) {
   EGN_CUDA(cudaMemsetAsync(not_ones, 0, sizeof(int), s));
+  if (in == nullptr) {   // implicit all-ones occupancy features
+    EGN_LAUNCH(ctx, "gather_input_features", (double)n * 4, 0, s, k_fill_ones<<<grid_for(n, 256), 256, 0, s>>>(out, n));
+    EGN_CUDA(cudaGetLastError());
+    return EGN_OK;
+  }
   EGN_LAUNCH(ctx, "gather_input_features", (double)n * 12, 0, s,
              k_gather_rows1<<<grid_for(n, 256), 256, 0, s>>>(in, perm, n, out, not_ones));
   EGN_CUDA(cudaGetLastError());

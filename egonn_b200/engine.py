@@ -87,6 +87,24 @@ class Engine:
         self.info = CoordsInfo(info.n_batches, info.n_input, list(info.n_rows))
         return self.info
 
+    def build_points(self, points: torch.Tensor, cloud_offsets: torch.Tensor, step, polar: bool) -> CoordsInfo:
+        """Fused ingest (egn_coords_build_points): concatenated raw points (n,3) f32 + (B+1) int32 first-point offsets,
+        both on the device -> quantised, de-duplicated, batched pyramid in one sort."""
+        _need_cuda(points, "points")
+        _need_cuda(cloud_offsets, "cloud_offsets")
+        pts = points.detach().to(torch.float32).contiguous()
+        off = cloud_offsets.detach().to(torch.int32).contiguous()
+        assert pts.dim() == 2 and pts.shape[1] == 3 and off.dim() == 1 and off.shape[0] >= 2
+        st = step if isinstance(step, (list, tuple)) else [step, step, step]
+        cstep = (C.c_float * 3)(*[float(v) for v in st])
+        info = L.CoordsInfo()
+        with torch.cuda.device(pts.device):
+            L.check(self.lib.egn_coords_build_points(self._ctx, _ptr(pts), pts.shape[0], _ptr(off), off.shape[0] - 1, cstep,
+                                                     int(polar), C.byref(info), _stream()))
+        self._coords_keepalive = (pts, off)
+        self.info = CoordsInfo(info.n_batches, info.n_input, list(info.n_rows))
+        return self.info
+
     def _new(self, shape, dtype):
         return torch.empty(shape, dtype=dtype, device=self.device)
 
@@ -112,10 +130,12 @@ class Engine:
 
     # -- whole forward -----------------------------------------------------------------------------------------
     def forward(self, net: L.Net, blob: torch.Tensor, features: torch.Tensor, want_global=True, want_local=True) -> Dict:
-        _need_cuda(features, "features")
         assert self.info is not None, "build() first"
-        f = features.detach().to(torch.float32).contiguous().reshape(-1)
-        assert f.shape[0] == self.info.n_input, "features must have one row per input coordinate"
+        f = None
+        if features is not None:
+            _need_cuda(features, "features")
+            f = features.detach().to(torch.float32).contiguous().reshape(-1)
+            assert f.shape[0] == self.info.n_input, "features must have one row per input coordinate"
         out: Dict[str, torch.Tensor] = {}
         g = d = k = s = None
         if want_global:

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "egn_ctx_destroy": (C.c_int, [_P]),
     "egn_quantize": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_float), C.c_int, _P, _P, C.POINTER(C.c_int64), _P]),
     "egn_coords_build": (C.c_int, [_P, _P, C.c_int64, C.POINTER(CoordsInfo), _P]),
+    "egn_coords_build_points": (C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.POINTER(C.c_float), C.c_int, C.POINTER(CoordsInfo), _P]),
     "egn_coords_get": (C.c_int, [_P, C.c_int, _P, _P]),
     "egn_coords_input_rows": (C.c_int, [_P, _P, _P]),
     "egn_coords_batch_offsets": (C.c_int, [_P, C.c_int, _P, _P]),

@@ -306,6 +306,29 @@ class MinkGL(nn.Module):
         return out
 
     @torch.no_grad()
+    def forward_points(self, points: torch.Tensor, cloud_offsets: torch.Tensor, disable_global_head=False,
+                       disable_local_head=False) -> Dict:
+        """Fused ingest + forward for the caller sequence of eval/evaluate.py:331-338: raw points of B clouds
+        concatenated ((n,3) f32, CUDA) + first-point offsets ((B+1,) int32, CUDA) -> the packed outputs of
+        ``forward_packed`` on the quantised, batched, all-ones-feature input - one sort, one host sync."""
+        assert not self.training, "egonn_b200 runs inference only: call model.eval()"
+        if not points.is_cuda:
+            raise RuntimeError("egonn_b200 has no CPU path: move the points to a CUDA device")
+        eng = self._engine_for(points.device)
+        blob, net = self._pack(points.device)
+        q = self.quantizer.describe()
+        with torch.cuda.device(points.device):
+            info = eng.build_points(points, cloud_offsets, q["step"], q["coordinates"] == "polar")
+            want_local = self.local_head is not None and not disable_local_head
+            out = eng.forward(net, blob, None, want_global=not disable_global_head, want_local=want_local)
+            if want_local:
+                lvl = out["local_level"]
+                out["local_coords"] = eng.level_coords(lvl)
+                out["local_offsets"] = eng.batch_offsets(lvl)
+        out["n_rows"] = info.n_rows
+        return out
+
+    @torch.no_grad()
     def forward(self, batch: Dict[str, torch.Tensor], disable_global_head: bool = False, disable_local_head: bool = False):
         p = self.forward_packed(batch, disable_global_head, disable_local_head)
         y = {}

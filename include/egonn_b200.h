@@ -84,6 +84,15 @@ typedef struct {
  * info (host) is filled; synchronises `stream` once. */
 int egn_coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n, egn_coords_info *info, egn_stream_t stream);
 
+/* Fused ingest: raw points -> pyramid in ONE sort.  Replaces the caller sequence eval/evaluate.py:331-335
+ * (quantizer(pc) per cloud, ME.utils.batched_coordinates, ones features) + the ME.SparseTensor build of
+ * models/minkgl.py:269.  points (n,3) f32 = n_clouds clouds concatenated; cloud_offsets (n_clouds+1) int32 DEVICE
+ * array of first-point indices (offsets[n_clouds] == n); step/polar as in egn_quantize.  The batch index of a voxel
+ * is its cloud; info->n_input = n points; the "input row" of a level-0 voxel is its first point.  egn_forward may
+ * then be called with features == NULL (all-ones occupancy features, what every reference caller feeds). */
+int egn_coords_build_points(egn_ctx *ctx, const float *points, int64_t n, const int32_t *cloud_offsets, int n_clouds,
+                            const float step[3], int polar, egn_coords_info *info, egn_stream_t stream);
+
 /* Copy the coordinates of level L (tensor stride 2^L) into out (n_rows[L],4) int32, canonical order. */
 int egn_coords_get(egn_ctx *ctx, int level, int32_t *out, egn_stream_t stream);
 /* Input row that became canonical L0 row r: out (n_rows[0]) int32. */
@@ -138,7 +147,7 @@ typedef struct {
  * Replaces: MinkGL.forward models/minkgl.py:267-315 (MinkTrunk.forward :136-153, MinkHead.forward :46-60,
  * ECABasicBlock.forward layers/eca_block.py:56-73, GeM.forward layers/pooling.py:82-86, the three
  * regressors/decoders and Quantizer.keypoint_position) and MinkLoc.forward models/minkloc.py:44-61.
- * Requires egn_coords_build on the same ctx.  features (n_input) f32 in INPUT row order.
+ * Requires egn_coords_build on the same ctx.  features (n_input) f32 in INPUT row order, or NULL = all ones.
  *   global_out       (n_batches, global dim) f32, or NULL to skip the global head
  *   desc_out         (n_rows[Llocal], desc dim) f32 |
  *   keypoints_out    (n_rows[Llocal], 3) f32        |  all NULL to skip the local head

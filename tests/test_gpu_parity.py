@@ -317,3 +317,30 @@ def test_tensor_core_1x1_conv(cin, cout, cuda):
     w = torch.randn(1, cin, cout, device=cuda) / np.sqrt(cin)
     y = eng.conv_tc(2, 1, x, w)
     assert_close_rel(y, x @ w[0], 2e-5, f"1x1 {cin}->{cout}")
+
+
+@pytest.mark.parametrize("case", ["mini3_cartesian", "mini2_polar"])
+def test_fused_points_ingest_matches_staged_path(case, cuda, weights):
+    """egn_coords_build_points (raw points -> pyramid in one sort, implicit ones features) == quantise per cloud ->
+    batched_coordinates -> forward, and the level-0 voxel set equals the golden quantisation."""
+    import egonn_b200 as E
+    g = load_golden(case)
+    quant = GOLDEN_CASES[case]
+    model, mp = _model(weights, quant, cuda)
+    sp = g["points_splits"]
+    pts = torch.from_numpy(g["points"]).to(cuda)
+    off = torch.tensor(sp, dtype=torch.int32, device=cuda)
+    a = model.forward_points(pts, off)
+    c0 = model._engine.level_coords(0).cpu().numpy()
+    rows = model._engine.input_rows().cpu().numpy()
+    if quant["coordinates"] == "cartesian":
+        assert np.array_equal(c0[lex_order(torch.from_numpy(c0))], g["coords"][me_ops.canonical_order(g["coords"])])
+        # the "input row" of a voxel is its FIRST point (sparse_quantize first-wins)
+        first = np.concatenate([g["quant_index"][g["coords"][:, 0] == b] + sp[b] for b in range(int(g["n_clouds"]))])
+        assert set(rows.tolist()) == set(first.tolist())
+    coords = [mp.quantizer(pts[sp[i]:sp[i + 1]])[0] for i in range(int(g["n_clouds"]))]
+    bc = E.batched_coordinates(coords)
+    b = model.forward_packed({"coords": bc, "features": torch.ones((bc.shape[0], 1), device=cuda)})
+    assert torch.equal(a["local_coords"], b["local_coords"]) and torch.equal(a["local_offsets"], b["local_offsets"])
+    for k in ("global", "descriptors", "keypoints", "sigma"):
+        assert_close_rel(a[k], b[k], 1e-6, k)
