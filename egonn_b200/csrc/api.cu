@@ -118,6 +118,9 @@ int egn_ctx_create(egn_ctx **out, int device) {
     delete ctx;
     return EGN_ERR_CUDA;
   }
+  cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   *out = ctx;
   return EGN_OK;
 }
@@ -131,6 +134,9 @@ int egn_ctx_destroy(egn_ctx *ctx) {
   ctx->feats.release();
   ctx->prof.drain();
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
+  if (ctx->aux) cudaStreamDestroy(ctx->aux);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->host) cudaFreeHost(ctx->host);
   if (ctx->dev_counts) cudaFree(ctx->dev_counts);
   delete ctx;

@@ -72,6 +72,8 @@ struct egn_ctx {
   egn::Taps taps;
   egn::Prof prof;
   bool use_tc = true;
+  cudaStream_t aux = nullptr;       // second stream: the local head overlaps the upper trunk levels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 // bracket one kernel class: counts the launch, and in profile mode records start/stop events

@@ -121,6 +121,33 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
   float *x[EGN_MAX_LEVELS] = {nullptr};
   x[0] = x0;
   const float *cur = x0;
+  // ---- local head (models/minkgl.py:288-308): needs only trunk levels <= max(local levels), so it is enqueued on the
+  //      context's second stream as soon as that level is done and overlaps the small upper trunk levels ----
+  auto run_local = [&](cudaStream_t ls) -> int {
+    Fwd F{ctx, net, weights, ls};
+    const egn_head &h = net->local_head;
+    float *lm = nullptr;
+    EGN_TRY(run_head(F, h, x, &lm));
+    const int lvl = h.levels[0];
+    const size_t n = py.n[lvl];
+    tp.lmap = lm; tp.c_l = h.out_channels; tp.lvl_l = lvl;
+    float *d1 = F.alloc(n * net->desc_mlp[0].cout), *d2 = F.alloc(n * net->desc_mlp[1].cout);
+    float *k1 = F.alloc(n * net->kp_mlp[0].cout), *k2 = F.alloc(n * net->kp_mlp[1].cout);
+    float *s1 = F.alloc(n * net->sigma_mlp[0].cout), *s2 = F.alloc(n * net->sigma_mlp[1].cout);
+    EGN_CHECK(d1 && d2 && k1 && k2 && s1 && s2, EGN_ERR_STATE, "feature arena exhausted (local mlps)");
+    EGN_CHECK(net->kp_mlp[1].cout == 3 && net->sigma_mlp[1].cout == 1, EGN_ERR_INVALID, "keypoint/sigma regressor shapes");
+    EGN_TRY(F.layer(net->desc_mlp[0], lvl, 1, 0, lm, 1, 0, d1));
+    EGN_TRY(F.layer(net->desc_mlp[1], lvl, 1, 0, d1, 0, 0, d2));
+    EGN_TRY(run_l2norm(ctx, d2, (int)n, net->desc_mlp[1].cout, desc_out, ls));
+    EGN_TRY(F.layer(net->kp_mlp[0], lvl, 1, 0, lm, 1, 0, k1));
+    EGN_TRY(F.layer(net->kp_mlp[1], lvl, 1, 0, k1, 0, 0, k2));
+    EGN_TRY(F.layer(net->sigma_mlp[0], lvl, 1, 0, lm, 1, 0, s1));
+    EGN_TRY(F.layer(net->sigma_mlp[1], lvl, 1, 0, s1, 0, 0, s2));
+    EGN_TRY(run_kp_sigma(ctx, lvl, k2, s2, net->polar, net->quant_step, net->ignore_keypoint_regressor, kp_out, sigma_out, ls));
+    return EGN_OK;
+  };
+  bool local_forked = false;
+  const int local_top = do_local ? net->local_head.levels[net->local_head.n_levels - 1] : -1;
   for (int L = 1; L <= net->n_levels; ++L) {
     const size_t n = py.n[L];
     const int c = net->conv2[L].cout;
@@ -151,6 +178,17 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
     cur = xo;
     tp.down[L] = d; tp.c_down[L] = net->down[L].cout;
     tp.block[L] = xo; tp.c_block[L] = c;
+    if (L == local_top) {
+      if (L < net->n_levels && ctx->aux && !ctx->prof.on) {               // fork: local head || levels L+1..n + global head
+        EGN_CUDA(cudaEventRecord(ctx->ev_fork, s));
+        EGN_CUDA(cudaStreamWaitEvent(ctx->aux, ctx->ev_fork, 0));
+        EGN_TRY(run_local(ctx->aux));
+        EGN_CUDA(cudaEventRecord(ctx->ev_join, ctx->aux));
+        local_forked = true;
+      } else {
+        EGN_TRY(run_local(s));
+      }
+    }
   }
 
   // ---- global head -> decoder -> pooling (models/minkgl.py:273-286) ----
@@ -177,28 +215,7 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
     EGN_TRY(run_pool(ctx, lvl, c, pin, mode, net->gem_p, net->gem_eps, part, slices, global_out, s));
   }
 
-  // ---- local head (models/minkgl.py:288-308) ----
-  if (do_local) {
-    const egn_head &h = net->local_head;
-    float *lm = nullptr;
-    EGN_TRY(run_head(F, h, x, &lm));
-    const int lvl = h.levels[0];
-    const size_t n = py.n[lvl];
-    tp.lmap = lm; tp.c_l = h.out_channels; tp.lvl_l = lvl;
-    float *d1 = F.alloc(n * net->desc_mlp[0].cout), *d2 = F.alloc(n * net->desc_mlp[1].cout);
-    float *k1 = F.alloc(n * net->kp_mlp[0].cout), *k2 = F.alloc(n * net->kp_mlp[1].cout);
-    float *s1 = F.alloc(n * net->sigma_mlp[0].cout), *s2 = F.alloc(n * net->sigma_mlp[1].cout);
-    EGN_CHECK(d1 && d2 && k1 && k2 && s1 && s2, EGN_ERR_STATE, "feature arena exhausted (local mlps)");
-    EGN_CHECK(net->kp_mlp[1].cout == 3 && net->sigma_mlp[1].cout == 1, EGN_ERR_INVALID, "keypoint/sigma regressor shapes");
-    EGN_TRY(F.layer(net->desc_mlp[0], lvl, 1, 0, lm, 1, 0, d1));
-    EGN_TRY(F.layer(net->desc_mlp[1], lvl, 1, 0, d1, 0, 0, d2));
-    EGN_TRY(run_l2norm(ctx, d2, (int)n, net->desc_mlp[1].cout, desc_out, s));
-    EGN_TRY(F.layer(net->kp_mlp[0], lvl, 1, 0, lm, 1, 0, k1));
-    EGN_TRY(F.layer(net->kp_mlp[1], lvl, 1, 0, k1, 0, 0, k2));
-    EGN_TRY(F.layer(net->sigma_mlp[0], lvl, 1, 0, lm, 1, 0, s1));
-    EGN_TRY(F.layer(net->sigma_mlp[1], lvl, 1, 0, s1, 0, 0, s2));
-    EGN_TRY(run_kp_sigma(ctx, lvl, k2, s2, net->polar, net->quant_step, net->ignore_keypoint_regressor, kp_out, sigma_out, s));
-  }
+  if (local_forked) EGN_CUDA(cudaStreamWaitEvent(s, ctx->ev_join, 0));   // join the local-head stream
   return EGN_OK;
 }
 

@@ -13,6 +13,7 @@
 // output row is written exactly once with the BatchNorm/ReLU/residual epilogue applied - no atomics, no
 // separate scatter pass, deterministic.
 #include <algorithm>
+#include <type_traits>
 
 #include "ctx.cuh"
 
@@ -183,23 +184,28 @@ __device__ __forceinline__ uint32_t morton6(int x, int y, int z) {  // x,y,z in 
 // feature row) of every present neighbour to its column of a shared-memory list.  Phase 2 (converged, heavy):
 // the warp loops to the longest list; each lane does 32 FMAs per neighbour with the kernel row W[t,:] read as
 // 8 conflict-free LDS.128 (row stride 36 floats).  Work is proportional to the PRESENT pairs (~18 of 125).
-constexpr int kC0Warps = 4;
 constexpr int kC0WStride = 36;
+// ONES = every input feature is 1.0f (what every EgoNN caller feeds): the list holds only the 7-bit offset index
+// (1 byte per pair -> 8 warps per CTA, 4 CTAs per SM) and the FMA degenerates to an add.  Both variants are launched;
+// the device-side flag written by the feature gather decides which one does the work (the other exits at once).
+template <bool ONES> struct C0 { static constexpr int kWarps = ONES ? 8 : 4; static constexpr int kCtas = ONES ? 4 : 2; };
 
-template <int KS>
-__global__ void __launch_bounds__(kC0Warps * 32, 2) k_conv0(const float *__restrict__ f0 /* (n0) canonical order */,
+template <int KS, bool ONES>
+__global__ void __launch_bounds__(C0<ONES>::kWarps * 32, C0<ONES>::kCtas) k_conv0(const float *__restrict__ f0 /* (n0) canonical order */,
                                                             const uint64_t *__restrict__ keys0, const int *__restrict__ up0,
                                                             const int *__restrict__ up1, const int *__restrict__ nbr2,
                                                             const uint64_t *__restrict__ mask64, const int *__restrict__ first0, int n0,
                                                             const float *__restrict__ w /* (KS^3,1,32) */, const float *__restrict__ scale,
                                                             const float *__restrict__ shift, int relu, const int *__restrict__ not_ones,
                                                             float *__restrict__ out) {
-  constexpr int KV = KS * KS * KS, R = KS / 2, COUT = 32;
-  const bool all_ones = not_ones != nullptr && *not_ones == 0;   // every input feature == 1.0f (what every EgoNN caller feeds)
+  constexpr int KV = KS * KS * KS, R = KS / 2, COUT = 32, kC0Warps = C0<ONES>::kWarps;
+  using entry_t = typename std::conditional<ONES, uint8_t, uint32_t>::type;
+  const bool all_ones = not_ones != nullptr && *not_ones == 0;
+  if (all_ones != ONES) return;
   extern __shared__ __align__(16) uint8_t s_raw[];
   float *s_w = (float *)s_raw;                                           // [KV][36]
   unsigned long long *s_box = (unsigned long long *)(s_w + KV * kC0WStride + 4);   // [axis 3][l 4][delta 3]
-  uint32_t *s_list = (uint32_t *)(s_box + 36);                           // [warp][KV][32]
+  entry_t *s_list = (entry_t *)(s_box + 36);                             // [warp][KV][32]
   for (int t = threadIdx.x; t < KV * COUT; t += blockDim.x) s_w[(t / COUT) * kC0WStride + (t % COUT)] = w[t];
   if (threadIdx.x < 36) {
     // 64-bit set of Morton-6 codes whose `axis` coordinate lies in window(l) /\ cell(delta)
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(kC0Warps * 32, 2) k_conv0(const float *__restr
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t *list = s_list + (size_t)warp * KV * 32;
+  entry_t *list = s_list + (size_t)warp * KV * 32;
   const int nwarps = gridDim.x * kC0Warps;
   for (int base = (blockIdx.x * kC0Warps + warp) * 32; base < n0; base += nwarps * 32) {
     const int r = base + lane;
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(kC0Warps * 32, 2) k_conv0(const float *__restr
           const int x = (b & 1) | ((b >> 2) & 2), y = ((b >> 1) & 1) | ((b >> 3) & 2), z = ((b >> 2) & 1) | ((b >> 4) & 2);
           const int t = (x + 4 * dx - lx + R) + KS * ((y + 4 * dy - ly + R) + KS * (z + 4 * dz - lz + R));
           const int frow = fb[i] + __popcll(occ[i] & ((1ull << b) - 1ull));
-          list[cnt * 32 + lane] = (uint32_t)t | ((uint32_t)frow << 7);
+          list[cnt * 32 + lane] = ONES ? (entry_t)t : (entry_t)((uint32_t)t | ((uint32_t)frow << 7));
           ++cnt;
         }
       }
@@ -267,7 +273,7 @@ __global__ void __launch_bounds__(kC0Warps * 32, 2) k_conv0(const float *__restr
     for (int i = 0; i < maxcnt; ++i) {
       if (i < cnt) {
         const uint32_t e = list[i * 32 + lane];
-        const float f = all_ones ? 1.f : f0[e >> 7];
+        const float f = ONES ? 1.f : f0[e >> 7];
         const float4 *wr = (const float4 *)(s_w + (e & 127u) * kC0WStride);
 #pragma unroll
         for (int c4 = 0; c4 < COUT / 4; ++c4) {
@@ -555,21 +561,30 @@ int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const fl
   const int n0 = py.n[0];
   EGN_CHECK(n0 <= (1 << 25), EGN_ERR_INVALID, "conv0: more than 2^25 voxels");
   const int kv = ksize * ksize * ksize;
-  const size_t smem = (size_t)(kv * kC0WStride + 4) * 4 + 36 * 8 + (size_t)kC0Warps * kv * 32 * 4;
-  const int blocks = (int)std::min<int64_t>(div_up(n0, kC0Warps * 32), (int64_t)kNumSMs * 2 * 4);
   const double pairs = (double)py.pairs_conv0;  // profile mode only (0 otherwise)
   const double bytes = pairs * (1 + cout) * 4 + pairs * 8 + (double)kv * cout * 4, flops = 2.0 * pairs * cout;
-  if (ksize == 5) {
-    static bool attr = false;
-    if (!attr) { EGN_CUDA(cudaFuncSetAttribute(k_conv0<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    EGN_LAUNCH(ctx, "conv0_5x5x5", bytes, flops, s,
-               k_conv0<5><<<blocks, kC0Warps * 32, smem, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], py.mask64, py.first0, n0, w,
-                                                              scale, shift, relu, not_ones, out));
-  } else {
-    EGN_LAUNCH(ctx, "conv0_3x3x3", bytes, flops, s,
-               k_conv0<3><<<blocks, kC0Warps * 32, smem, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], py.mask64, py.first0, n0, w,
-                                                              scale, shift, relu, not_ones, out));
+  const size_t fixed = (size_t)(kv * kC0WStride + 4) * 4 + 36 * 8;
+  const size_t smem1 = fixed + (size_t)C0<true>::kWarps * kv * 32, smem0 = fixed + (size_t)C0<false>::kWarps * kv * 32 * 4;
+  const int blocks1 = (int)std::min<int64_t>(div_up(n0, C0<true>::kWarps * 32), (int64_t)kNumSMs * C0<true>::kCtas * 4);
+  const int blocks0 = (int)std::min<int64_t>(div_up(n0, C0<false>::kWarps * 32), (int64_t)kNumSMs * C0<false>::kCtas * 4);
+#define EGN_C0(KS, NAME)                                                                                                    \
+  {                                                                                                                         \
+    static bool attr = false;                                                                                               \
+    if (!attr) {                                                                                                            \
+      EGN_CUDA(cudaFuncSetAttribute(k_conv0<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));           \
+      EGN_CUDA(cudaFuncSetAttribute(k_conv0<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));          \
+      attr = true;                                                                                                          \
+    }                                                                                                                       \
+    if (not_ones)                                                                                                           \
+      EGN_LAUNCH(ctx, NAME, bytes, flops, s,                                                                                \
+                 k_conv0<KS, true><<<blocks1, C0<true>::kWarps * 32, smem1, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], \
+                                                                                 py.mask64, py.first0, n0, w, scale, shift, relu, not_ones, out)); \
+    EGN_LAUNCH(ctx, not_ones ? NAME "(general variant)" : NAME, not_ones ? 0.0 : bytes, not_ones ? 0.0 : flops, s,          \
+               k_conv0<KS, false><<<blocks0, C0<false>::kWarps * 32, smem0, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], \
+                                                                                py.mask64, py.first0, n0, w, scale, shift, relu, not_ones, out)); \
   }
+  if (ksize == 5) EGN_C0(5, "conv0_5x5x5") else EGN_C0(3, "conv0_3x3x3")
+#undef EGN_C0
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
 }
