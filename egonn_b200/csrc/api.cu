@@ -1,5 +1,6 @@
 // extern "C" surface of libegonn_b200.so (declared in include/egonn_b200.h) + context / arena plumbing.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "ctx.cuh"
@@ -119,6 +120,11 @@ int egn_ctx_create(egn_ctx **out, int device) {
     return EGN_ERR_CUDA;
   }
   cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking);
+  const char *ks = getenv("EGN_KSPLIT");
+  ctx->ksplit = ks && ks[0] == '1';
+  if (const char *t = getenv("EGN_TRACE")) if (t[0] == '1') { cudaMalloc(&ctx->trace, 64 * 8 * 8); cudaMemset(ctx->trace, 0, 64 * 8 * 8); }
+  if (const char *h = getenv("EGN_HINT_P")) ctx->hint_producer = (unsigned)atoi(h);
+  if (const char *h = getenv("EGN_HINT_S")) ctx->hint_single = (unsigned)atoi(h);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
   cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   *out = ctx;
@@ -134,6 +140,7 @@ int egn_ctx_destroy(egn_ctx *ctx) {
   ctx->feats.release();
   ctx->prof.drain();
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
+  if (ctx->splitk_buf) cudaFree(ctx->splitk_buf);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -194,10 +201,41 @@ int egn_coords_neighbors(egn_ctx *ctx, int level, int32_t *out, egn_stream_t str
   return EGN_OK;
 }
 
+static void apply_window(egn_ctx *ctx, cudaStream_t s) {
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof(v));
+  v.accessPolicyWindow.base_ptr = const_cast<void *>(ctx->win_ptr);
+  v.accessPolicyWindow.num_bytes = ctx->win_bytes;
+  v.accessPolicyWindow.hitRatio = 1.0f;
+  v.accessPolicyWindow.hitProp = ctx->win_bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v);   // best effort
+  cudaGetLastError();
+}
+
+int egn_weights_resident(egn_ctx *ctx, const void *weights, size_t bytes) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  cudaDeviceProp prop;
+  EGN_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+  size_t want = bytes;
+  if (want > (size_t)prop.persistingL2CacheMaxSize) want = (size_t)prop.persistingL2CacheMaxSize;
+  if (want > (size_t)prop.accessPolicyMaxWindowSize) want = (size_t)prop.accessPolicyMaxWindowSize;
+  if (bytes) EGN_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want));
+  ctx->win_ptr = bytes ? weights : nullptr;
+  ctx->win_bytes = bytes ? want : 0;
+  if (!bytes) cudaCtxResetPersistingL2Cache();
+  return EGN_OK;
+}
+
 int egn_forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float *features, float *global_out,
                 float *desc_out, float *keypoints_out, float *sigma_out, egn_stream_t stream) {
   EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
   DeviceGuard g(ctx->device);
+  if (ctx->win_ptr) {
+    apply_window(ctx, (cudaStream_t)stream);
+    if (ctx->aux) apply_window(ctx, ctx->aux);
+  }
   return forward(ctx, net, weights, features, global_out, desc_out, keypoints_out, sigma_out, (cudaStream_t)stream);
 }
 
@@ -258,6 +296,13 @@ int egn_profile_read(egn_ctx *ctx, egn_profile_entry *out, int capacity, int *n_
 }
 
 int64_t egn_launch_count(egn_ctx *ctx) { return ctx ? ctx->prof.launches : 0; }
+
+/* debug: copy the k_sconv_tc timeline (EGN_TRACE=1) to host memory: 64 chunks x 8 clock64 stamps */
+int egn_debug_trace(egn_ctx *ctx, long long *host_out) {
+  EGN_CHECK(ctx && ctx->trace && host_out, EGN_ERR_STATE, "trace buffer not allocated (EGN_TRACE=1)");
+  EGN_CUDA(cudaMemcpy(host_out, ctx->trace, 64 * 8 * 8, cudaMemcpyDeviceToHost));
+  return EGN_OK;
+}
 
 int egn_topk_smallest(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out, egn_stream_t stream) {
   return op_topk(sigma, offsets, n_batches, k, idx_out, (cudaStream_t)stream);

@@ -74,6 +74,13 @@ struct egn_ctx {
   bool use_tc = true;
   cudaStream_t aux = nullptr;       // second stream: the local head overlaps the upper trunk levels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  const void *win_ptr = nullptr;    // persisting-L2 window over the weight blob (egn_weights_resident)
+  size_t win_bytes = 0;
+  unsigned hint_producer = 20000, hint_single = 20000;   // mbarrier try_wait suspend hints (EGN_HINT_P / EGN_HINT_S)
+  void *trace = nullptr;            // debug timeline buffer for k_sconv_tc (EGN_TRACE=1 allocates 64*8 int64)
+  bool ksplit = false;              // K-split of small 128-channel levels (EGN_KSPLIT=1)
+  void *splitk_buf = nullptr;       // raw partial tiles of K-split convolutions (small levels only)
+  size_t splitk_cap = 0;
 };
 
 // bracket one kernel class: counts the launch, and in profile mode records start/stop events

@@ -40,19 +40,34 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// hint_ns > 0: try_wait may suspend the thread in hardware up to hint_ns; 0: plain polling try_wait
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, uint32_t hint_ns) {
   uint32_t done;
-  do {   // try_wait suspends the thread in hardware until the phase flips or the hint (ns) expires - no busy polling
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t"
-        "}"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
-        : "memory");
-  } while (!done);
+  if (hint_ns) {
+    do {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}"
+          : "=r"(done)
+          : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+          : "memory");
+    } while (!done);
+  } else {
+    do {
+      asm volatile(
+          "{\n\t"
+          ".reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t"
+          "}"
+          : "=r"(done)
+          : "r"(smem_u32(bar)), "r"(parity)
+          : "memory");
+    } while (!done);
+  }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -83,6 +98,18 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
       "}" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// one lane of a fully converged warp (the compiler keeps operands of the guarded instruction in uniform registers)
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
 }
 __device__ __forceinline__ void umma_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -138,7 +165,9 @@ struct Args {
   float *out;
   const uint8_t *wpack;  // [n_chunks][hi|lo][COUT][64] bf16, swizzled shared-memory images
   const float *scale, *shift;
-  int n_out, relu, accumulate, mode;  // mode 0: identity rows (1x1x1 convolution), 1: 27-neighbour table, 2: 2x2x2 stride-2 children, 3: transposed 2x2x2 (parent, slice = own code)
+  long long *trace;                      // debug: clock64 timeline of CTA 0 (null in production)
+  uint32_t hint_producer, hint_single;   // try_wait suspend hints (ns) for the gather warps / the TMA and MMA threads
+  int n_out, relu, accumulate, cout_total, ksplit, mode;   // ksplit > 1: grid.z partitions the chunks, raw partials to out + z*n_out*cout_total  // mode 0: identity rows (1x1x1 convolution), 1: 27-neighbour table, 2: 2x2x2 stride-2 children, 3: transposed 2x2x2 (parent, slice = own code)
   const int *nbr;
   const int *cstart;
   const uint32_t *cmask;
@@ -146,16 +175,24 @@ struct Args {
   const uint64_t *keys;    // mode 3: key of every output row (kernel slice = key & 7)
 };
 
-// COUT <= 64: two CTAs per SM (2 stages, 8 producer warps each); COUT == 128: one CTA (3 stages, 16 producer warps)
+// Shared-memory plan.  A stages (gathered activations, 32 KB each) and the B ring (weight chunks, 256*COUT bytes each)
+// are separate rings: weight chunks do not depend on anything but a free slot, so the TMA thread runs kBSlots chunks
+// ahead and the ~2.5 us bulk-copy latency leaves the per-chunk critical path.
+//   COUT == 128          : 1 CTA/SM, 16 gather warps, 3 A stages + 3 B slots (32 KB each)
+//   CIN == 128, COUT < 128 (N-split of small levels): 1 CTA/SM, 16 gather warps, 3 A stages + deep B ring
+//   otherwise            : 2 CTAs/SM, 8 gather warps, 2 A stages + 2..4 B slots
 template <int CIN, int COUT>
 struct Cfg {
-  static constexpr int kStages = COUT == 128 ? 3 : 2;
-  static constexpr int kProducerWarps = COUT == 128 ? 16 : 8;
-  static constexpr int kCtasPerSm = COUT == 128 ? 1 : 2;
+  static constexpr bool kBig = COUT == 128 || CIN == 128;
+  static constexpr int kStages = kBig ? 3 : 2;
+  static constexpr int kProducerWarps = kBig ? 16 : 8;
+  static constexpr int kCtasPerSm = kBig ? 1 : 2;
+  static constexpr int kPrefetch = 1;                               // chunks gathered ahead in registers
   static constexpr int kThreads = (kProducerWarps + 2) * 32;
-  static constexpr int kBBytes = 2 * COUT * 128;                  // hi + lo image of one weight chunk
-  static constexpr int kStageBytes = 2 * kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kRows * 27 * 4 + 2 * COUT * 4 + 512;
+  static constexpr int kBBytes = 2 * COUT * 128;                    // hi + lo image of one weight chunk
+  static constexpr int kBSlots = COUT == 128 ? 3 : (CIN == 128 ? (COUT == 64 ? 6 : 8) : (COUT == 32 ? 4 : 2));
+  static constexpr int kABytesAll = kStages * 2 * kABytes;
+  static constexpr int kSmemBytes = kABytesAll + kBSlots * kBBytes + kRows * 27 * 4 + 2 * COUT * 4 + 768;
 };
 
 template <int CIN, int COUT, int KOFF>
@@ -169,13 +206,17 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   constexpr int NBR_ITERS = (kRows * KOFF + NT - 1) / NT;
   // dynamic shared memory starts 1024-byte aligned (checked below): SWIZZLE_128B tiles need it
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t *tiles = smem;
-  int *s_nbr = (int *)(smem + kStages * C::kStageBytes);          // [kRows][KOFF]
+  constexpr int kBSlots = C::kBSlots;
+  uint8_t *tiles = smem;                                          // A stages: [kStages][hi 16 KB | lo 16 KB]
+  uint8_t *btiles = smem + C::kABytesAll;                         // B ring:   [kBSlots][hi | lo] (COUT*128 bytes each image)
+  int *s_nbr = (int *)(btiles + kBSlots * C::kBBytes);            // [kRows][KOFF]
   float *s_scale = (float *)(s_nbr + kRows * 27);                 // [COUT]
   float *s_shift = s_scale + COUT;                                // [COUT]
-  uint64_t *full = (uint64_t *)(s_shift + COUT);                  // [kStages]
-  uint64_t *empty = full + kStages;                               // [kStages]
-  uint64_t *accum = empty + kStages;                              // [1]
+  uint64_t *full = (uint64_t *)(s_shift + COUT);                  // [kStages]  A stage written by the gather warps
+  uint64_t *empty = full + kStages;                               // [kStages]  A stage consumed by the tensor core
+  uint64_t *bfull = empty + kStages;                              // [kBSlots]  weight chunk landed (TMA transaction bytes)
+  uint64_t *bempty = bfull + kBSlots;                             // [kBSlots]  weight chunk consumed
+  uint64_t *accum = bempty + kBSlots;                             // [1]
   uint32_t *s_tmem = (uint32_t *)(accum + 1);
   int *s_nlist = (int *)(s_tmem + 1);
   uint32_t *s_present = (uint32_t *)(s_nlist + 1);                // [2] bit j: chunk j has at least one present row
@@ -183,12 +224,17 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kRows;
+  const int col0 = blockIdx.y * COUT;     // N-split: this CTA computes output channels [col0, col0 + COUT)
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], NPW + 1);   // one arrive per gather warp + the TMA thread's arrive.expect_tx
+      mbar_init(&full[s], NPW);       // one arrive per gather warp
       mbar_init(&empty[s], 1);        // one tcgen05.commit
+    }
+    for (int s = 0; s < kBSlots; ++s) {
+      mbar_init(&bfull[s], 1);        // the TMA thread's arrive.expect_tx
+      mbar_init(&bempty[s], 1);       // one tcgen05.commit
     }
     mbar_init(accum, 1);
     fence_barrier_init();
@@ -200,8 +246,8 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   for (int c = tid; c < COUT; c += NT) {
-    s_scale[c] = a.scale ? a.scale[c] : 1.f;
-    s_shift[c] = a.shift ? a.shift[c] : 0.f;
+    s_scale[c] = a.scale ? a.scale[col0 + c] : 1.f;
+    s_shift[c] = a.shift ? a.shift[col0 + c] : 0.f;
   }
   __syncthreads();                    // s_present zeroed before the atomics below
   // neighbour rows of the tile: all global loads first, then the shared stores (one latency, not NBR_ITERS)
@@ -248,8 +294,10 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   __syncthreads();
   tc_fence_after();
   if (tid == 0) {
+    // K-split: this CTA owns chunks [j_lo, j_hi) of the reduction
+    const int j_lo = (int)(((int64_t)NCH * blockIdx.z) / a.ksplit), j_hi = (int)(((int64_t)NCH * (blockIdx.z + 1)) / a.ksplit);
     int n = 0;
-    for (int j = 0; j < NCH; ++j)
+    for (int j = j_lo; j < j_hi; ++j)
       if ((s_present[j >> 5] >> (j & 31)) & 1u) s_list[n++] = j;
     *s_nlist = n;
   }
@@ -264,7 +312,6 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     const int g = tid & 7, rs = tid >> 3;
     const int sw_off = rs * 128 + ((g ^ (rs & 7)) << 4);
     const int *my_nbr = s_nbr + rs * KOFF;
-    float4 va[F], vb[F];
     auto issue = [&](int j, float4 (&da)[F], float4 (&db)[F]) {
       int koff, coff;                      // kernel offset and float offset inside the source row for this thread
       if (CIN == 32) { koff = 2 * j + (g >> 2); coff = (g & 3) * 8; }
@@ -279,44 +326,64 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
         ldg8_pred(a.in + (size_t)(pr ? src : 0) * CIN + coff, pr, da[p], db[p]);
       }
     };
-    if (nlist > 0) issue(s_list[0], va, vb);
-    for (int i = 0; i < nlist; ++i) {
-      const int s = i % kStages;
-      const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-      float4 na[F], nb[F];
-      if (i + 1 < nlist) issue(s_list[i + 1], na, nb);     // loads of the next chunk fly while this one is converted
-      mbar_wait(&empty[s], ph ^ 1u);
-      uint8_t *a_hi = tiles + s * C::kStageBytes + sw_off, *a_lo = a_hi + kABytes;
+    // register ring of PF+1 chunk buffers: the gathers of chunks i+1..i+PF are in flight while chunk i is converted
+    constexpr int PF = C::kPrefetch;
+    float4 ra[PF + 1][F], rb[PF + 1][F];
 #pragma unroll
-      for (int p = 0; p < F; ++p) {
-        uint4 hi, lo;
-        split2(va[p].x, va[p].y, hi.x, lo.x);
-        split2(va[p].z, va[p].w, hi.y, lo.y);
-        split2(vb[p].x, vb[p].y, hi.z, lo.z);
-        split2(vb[p].z, vb[p].w, hi.w, lo.w);
-        *(uint4 *)(a_hi + p * RSTEP * 128) = hi;
-        *(uint4 *)(a_lo + p * RSTEP * 128) = lo;
+    for (int d = 0; d < PF; ++d)
+      if (d < nlist) issue(s_list[d], ra[d], rb[d]);
+    for (int i0 = 0; i0 < nlist; i0 += PF + 1) {
+#pragma unroll
+      for (int u = 0; u <= PF; ++u) {                       // u is a compile-time ring index: buffers stay in registers
+        const int i = i0 + u;
+        if (i < nlist) {
+          const int s = i % kStages;
+          const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+          if (i + PF < nlist) issue(s_list[i + PF], ra[(u + PF) % (PF + 1)], rb[(u + PF) % (PF + 1)]);
+          const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0 && i < 64;
+          if (tr) a.trace[i * 8 + 5] = clock64();
+          mbar_wait(&empty[s], ph ^ 1u, a.hint_producer);
+          if (tr) a.trace[i * 8 + 6] = clock64();
+          uint8_t *a_hi = tiles + s * (2 * kABytes) + sw_off, *a_lo = a_hi + kABytes;
+#pragma unroll
+          for (int p = 0; p < F; ++p) {
+            uint4 hi, lo;
+            split2(ra[u][p].x, ra[u][p].y, hi.x, lo.x);
+            split2(ra[u][p].z, ra[u][p].w, hi.y, lo.y);
+            split2(rb[u][p].x, rb[u][p].y, hi.z, lo.z);
+            split2(rb[u][p].z, rb[u][p].w, hi.w, lo.w);
+            *(uint4 *)(a_hi + p * RSTEP * 128) = hi;
+            *(uint4 *)(a_lo + p * RSTEP * 128) = lo;
+          }
+          fence_proxy_async();            // this thread's generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();                   // ... of all 32 lanes, then ONE mbarrier arrive per warp instead of 32
+          if (lane == 0) mbar_arrive(&full[s]);
+          if (tr) a.trace[i * 8 + 7] = clock64();
+        }
       }
-      fence_proxy_async();            // this thread's generic-proxy writes -> visible to the tensor core (async proxy)
-      __syncwarp();                   // ... of all 32 lanes, then ONE mbarrier arrive per warp instead of 32
-      if (lane == 0) mbar_arrive(&full[s]);
-#pragma unroll
-      for (int p = 0; p < F; ++p) { va[p] = na[p]; vb[p] = nb[p]; }
     }
     // ===================== epilogue: TMEM -> scale/shift/relu -> global =====================
     // warp w reads TMEM lane quarter (w & 3) and the column group (w >> 2)
-    constexpr int CPW = COUT / (NPW / 4);
-    mbar_wait(accum, 0u);
-    tc_fence_after();
+    constexpr int CPW = (COUT / (NPW / 4)) >= 16 ? COUT / (NPW / 4) : 16;   // tcgen05.ld granularity: 16 columns
+    if (nlist > 0) {
+      mbar_wait(accum, 0u, a.hint_producer);
+      tc_fence_after();
+    }
     const int q = warp & 3, cg = warp >> 2;
     const int row = row0 + q * 32 + lane;
+    float *obase = a.out + (size_t)blockIdx.z * a.n_out * a.cout_total;
 #pragma unroll
     for (int cc = 0; cc < CPW; cc += 16) {
       const int c0 = cg * CPW + cc;
+      if (c0 >= COUT) break;                                                 // more gather warps than column groups
       uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      if (nlist > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = 0u;             // no chunk of this split touches the tile: partial = 0
+      }
       if (row < a.n_out) {
-        float *o = a.out + (size_t)row * COUT + c0;
+        float *o = obase + (size_t)row * a.cout_total + col0 + c0;
 #pragma unroll
         for (int gg = 0; gg < 4; ++gg) {
           float4 y;
@@ -338,40 +405,57 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     }
     tc_fence_before();
   } else if (warp == NPW) {
-    // ===================== B loader: one bulk copy per chunk =====================
+    // ===================== B loader: runs kBSlots chunks ahead of the tensor core =====================
     if (lane == 0) {
       for (int i = 0; i < nlist; ++i) {
         const int j = s_list[i];
-        const int s = i % kStages;
-        const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-        mbar_wait(&empty[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full[s], (uint32_t)C::kBBytes);
-        bulk_g2s(tiles + s * C::kStageBytes + 2 * kABytes, a.wpack + (size_t)j * C::kBBytes, (uint32_t)C::kBBytes, &full[s]);
+        const int sb = i % kBSlots;
+        const uint32_t ph = (uint32_t)(i / kBSlots) & 1u;
+        mbar_wait(&bempty[sb], ph ^ 1u, a.hint_single);
+        mbar_arrive_expect_tx(&bfull[sb], (uint32_t)C::kBBytes);
+        // this CTA's COUT rows of the hi image and of the lo image of chunk j (contiguous when COUT == cout_total)
+        const uint8_t *src = a.wpack + (size_t)j * 2 * a.cout_total * 128 + (size_t)col0 * 128;
+        uint8_t *dst = btiles + sb * C::kBBytes;
+        bulk_g2s(dst, src, (uint32_t)(COUT * 128), &bfull[sb]);
+        bulk_g2s(dst + COUT * 128, src + (size_t)a.cout_total * 128, (uint32_t)(COUT * 128), &bfull[sb]);
       }
     }
   } else {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(COUT);
-      for (int i = 0; i < nlist; ++i) {
-        const int s = i % kStages;
-        const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-        mbar_wait(&full[s], ph);
-        tc_fence_after();
-        const uint32_t sa = smem_u32(tiles + s * C::kStageBytes);
-        const uint32_t sb = sa + 2 * kABytes;
+    // The WHOLE warp walks the loop converged, so barrier addresses and matrix descriptors are warp-uniform values
+    // (uniform registers); only the tcgen05 instructions themselves are issued by one elected lane.  With the loop
+    // under `if (lane == 0)` the compiler wrapped every UTCHMMA in an ELECT + 5x R2UR.BROADCAST + branch sequence:
+    // ~80 cycles per MMA, which made this thread - not the gathers, not the weights - the bottleneck.
+    constexpr uint32_t idesc = umma_idesc(COUT);
+    for (int i = 0; i < nlist; ++i) {
+      const int s = i % kStages, sb = i % kBSlots;
+      const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i < 64 && lane == 0;
+      if (tr) a.trace[i * 8 + 0] = clock64();
+      mbar_wait(&bfull[sb], (uint32_t)(i / kBSlots) & 1u, a.hint_single);
+      if (tr) a.trace[i * 8 + 1] = clock64();
+      mbar_wait(&full[s], (uint32_t)(i / kStages) & 1u, a.hint_single);
+      if (tr) a.trace[i * 8 + 2] = clock64();
+      tc_fence_after();
+      const uint32_t sa = smem_u32(tiles + s * (2 * kABytes));
+      const uint32_t sbm = smem_u32(btiles + sb * C::kBBytes);
+      const uint32_t first = i == 0 ? 0u : 1u;
+      if (elect_one_sync()) {
 #pragma unroll
         for (int ks = 0; ks < kChunk / 16; ++ks) {
           const uint64_t ahi = umma_desc(sa + ks * 32), alo = umma_desc(sa + kABytes + ks * 32);
-          const uint64_t bhi = umma_desc(sb + ks * 32), blo = umma_desc(sb + COUT * 128 + ks * 32);
-          umma_f16(tmem_base, ahi, bhi, idesc, (i | ks) ? 1u : 0u);
+          const uint64_t bhi = umma_desc(sbm + ks * 32), blo = umma_desc(sbm + COUT * 128 + ks * 32);
+          umma_f16(tmem_base, ahi, bhi, idesc, ks == 0 ? first : 1u);
           umma_f16(tmem_base, alo, bhi, idesc, 1u);
           umma_f16(tmem_base, ahi, blo, idesc, 1u);
         }
-        umma_commit(&empty[s]);          // stage reusable once these MMAs have read it
+        umma_commit(&empty[s]);          // A stage and B slot reusable once these MMAs have read them
+        umma_commit(&bempty[sb]);
       }
-      umma_commit(accum);                // accumulator complete
+      __syncwarp();
+      if (tr) a.trace[i * 8 + 4] = clock64();
     }
+    if (nlist > 0 && elect_one_sync()) umma_commit(accum);   // accumulator complete
+    __syncwarp();
   }
   __syncthreads();
   if (warp == NPW + 1) {
@@ -388,10 +472,24 @@ static int launch(egn_ctx *ctx, const Args &a, const char *name, double bytes, d
     EGN_CUDA(cudaFuncSetAttribute(k_sconv_tc<CIN, COUT, KOFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_done = true;
   }
-  const int grid = (int)div_up(a.n_out, kRows);
+  const dim3 grid((unsigned)div_up(a.n_out, kRows), (unsigned)(a.cout_total / COUT), (unsigned)a.ksplit);
   EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv_tc<CIN, COUT, KOFF><<<grid, C::kThreads, C::kSmemBytes, s>>>(a));
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
+}
+
+// K-split finish: out = epilogue(sum_z partial[z]) in fixed z order (deterministic)
+__global__ void k_splitk_finish(const float4 *__restrict__ part, int splits, int64_t n4 /* rows*C/4 */, int c4, const float *__restrict__ scale,
+                                const float *__restrict__ shift, int relu, float4 *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 v = part[i];
+    for (int z = 1; z < splits; ++z) { const float4 p = part[i + z * n4]; v.x += p.x; v.y += p.y; v.z += p.z; v.w += p.w; }
+    const int c = (int)(i % c4) * 4;
+    if (scale) { v.x *= scale[c]; v.y *= scale[c + 1]; v.z *= scale[c + 2]; v.w *= scale[c + 3]; }
+    if (shift) { v.x += shift[c]; v.y += shift[c + 1]; v.z += shift[c + 2]; v.w += shift[c + 3]; }
+    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    out[i] = v;
+  }
 }
 
 }  // namespace tc
@@ -419,7 +517,7 @@ int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, 
   EGN_CHECK(((uintptr_t)wpack & 15) == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, EGN_ERR_INVALID,
             "tensor-core conv: pointers must be 16-byte aligned");
   tc::Args a = {};
-  a.in = in; a.out = out; a.wpack = (const uint8_t *)wpack; a.scale = scale; a.shift = shift; a.relu = relu; a.accumulate = accumulate;
+  a.in = in; a.out = out; a.wpack = (const uint8_t *)wpack; a.scale = scale; a.shift = shift; a.relu = relu; a.accumulate = accumulate; a.cout_total = cout; a.ksplit = 1; a.hint_producer = ctx->hint_producer; a.hint_single = ctx->hint_single; a.trace = (long long *)ctx->trace;
   long long pairs;
   char name[48];
   if (ksize == 1) {
@@ -448,6 +546,42 @@ int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, 
   const double bytes = ksize == 1 ? (double)pairs * (cin + cout) * 4
                                   : (double)pairs * (cin + cout) * 4 + (double)pairs * 8 + (double)K * cin * cout * 4;
   const double flops = 2.0 * pairs * cin * cout;
+  // small 128-channel levels: split the output channels over 2 or 4 CTAs per row tile (each streams only its share of
+  // the weight chunks) so that a 12..148-tile level spreads over the whole GPU
+  // and the 27 offsets over 3 CTAs (K-split): the 54-chunk serial chain per CTA becomes 18.  The raw partials go to the
+  // scratch arena and k_splitk_finish adds them in fixed order and applies the BatchNorm/ReLU epilogue (deterministic).
+  if (cin == 128 && cout == 128 && (ksize == 3 || ksize == 2) && !accumulate) {
+    const int tiles = (int)div_up(a.n_out, tc::kRows);
+    if (tiles <= 74) {        // N = 32 -> <= 148 CTAs for <= 37 tiles; N = 64 -> <= 148 CTAs for <= 74 tiles
+      const int splits = !ctx->ksplit ? 1 : (ksize == 3 ? (tiles <= 37 ? 3 : 1) : 1);
+      tc::Args b = a;
+      float *part = nullptr;
+      if (splits > 1) {
+        const size_t bytes_part = (size_t)splits * a.n_out * cout * 4;
+        if (ctx->splitk_cap < bytes_part) {
+          EGN_CUDA(cudaStreamSynchronize(s));
+          if (ctx->splitk_buf) EGN_CUDA(cudaFree(ctx->splitk_buf));
+          ctx->splitk_buf = nullptr; ctx->splitk_cap = 0;
+          EGN_CUDA(cudaMalloc((void **)&ctx->splitk_buf, bytes_part * 2));
+          ctx->splitk_cap = bytes_part * 2;
+        }
+        part = (float *)ctx->splitk_buf;
+        b.out = part; b.scale = nullptr; b.shift = nullptr; b.relu = 0; b.ksplit = splits;
+      }
+      int st;
+      if (tiles <= 37) st = ksize == 3 ? tc::launch<128, 32, 27>(ctx, b, name, bytes, flops, s) : tc::launch<128, 32, 8>(ctx, b, name, bytes, flops, s);
+      else st = ksize == 3 ? tc::launch<128, 64, 27>(ctx, b, name, bytes, flops, s) : tc::launch<128, 64, 8>(ctx, b, name, bytes, flops, s);
+      EGN_TRY(st);
+      if (splits > 1) {
+        const int64_t n4 = (int64_t)a.n_out * cout / 4;
+        EGN_LAUNCH(ctx, "splitk_finish", (double)(splits + 1) * a.n_out * cout * 4, 0, s,
+                   tc::k_splitk_finish<<<grid_for(n4, 256), 256, 0, s>>>((const float4 *)part, splits, n4, cout / 4, scale, shift, relu,
+                                                                          (float4 *)out));
+        EGN_CUDA(cudaGetLastError());
+      }
+      return EGN_OK;
+    }
+  }
 #define EGN_TC_CASE(KS, KO, CI, CO) \
   if (ksize == KS && cin == CI && cout == CO) return tc::launch<CI, CO, KO>(ctx, a, name, bytes, flops, s);
   EGN_TC_CASE(3, 27, 32, 32)

@@ -128,6 +128,13 @@ class Engine:
         L.check(self.lib.egn_coords_neighbors(self._ctx, level, _ptr(out), _stream()))
         return out
 
+    def weights_resident(self, blob: Optional[torch.Tensor]):
+        """Pin the weight blob in L2 (persisting access-policy window) for this context's forwards."""
+        if blob is None:
+            L.check(self.lib.egn_weights_resident(self._ctx, None, 0))
+        else:
+            L.check(self.lib.egn_weights_resident(self._ctx, _ptr(blob), blob.numel() * blob.element_size()))
+
     # -- whole forward -----------------------------------------------------------------------------------------
     def forward(self, net: L.Net, blob: torch.Tensor, features: torch.Tensor, want_global=True, want_local=True) -> Dict:
         assert self.info is not None, "build() first"

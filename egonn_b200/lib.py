@@ -60,6 +60,7 @@ _SIGNATURES = {
     "egn_coords_input_rows": (C.c_int, [_P, _P, _P]),
     "egn_coords_batch_offsets": (C.c_int, [_P, C.c_int, _P, _P]),
     "egn_coords_neighbors": (C.c_int, [_P, C.c_int, _P, _P]),
+    "egn_weights_resident": (C.c_int, [_P, _P, C.c_size_t]),
     "egn_forward": (C.c_int, [_P, C.POINTER(Net), _P, _P, _P, _P, _P, _P, _P]),
     "egn_forward_tap": (C.c_int, [_P, C.c_int, C.c_int, _P, _P]),
     "egn_conv": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P]),
@@ -70,6 +71,7 @@ _SIGNATURES = {
     "egn_profile_enable": (C.c_int, [_P, C.c_int]),
     "egn_profile_read": (C.c_int, [_P, C.POINTER(ProfileEntry), C.c_int, C.POINTER(C.c_int), C.c_int]),
     "egn_launch_count": (C.c_int64, [_P]),
+    "egn_debug_trace": (C.c_int, [_P, _P]),
     "egn_topk_smallest": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)

@@ -258,6 +258,7 @@ class MinkGL(nn.Module):
             self.local_descriptor_decoder = DescriptorDecoder(c, local_descriptor_size, normalize=local_normalize)
         self.quantizer = quantizer
         self.ignore_keypoint_regressor = False
+        self.l2_resident_weights = True   # keep the 37 MB weight blob in a persisting L2 window (egn_weights_resident)
         self._engine: Optional[Engine] = None
         self._packed = None       # (signature, blob on device, Net)
         self.last: Dict = {}      # extras of the last forward: local coordinates, batch offsets, level sizes
@@ -276,6 +277,8 @@ class MinkGL(nn.Module):
                                      ignore_keypoint_regressor=self.ignore_keypoint_regressor,
                                      bn_eps=self.trunk.bn["0"].bn.eps)
             self._packed = (sig, blob.to(device), net)
+            if self.l2_resident_weights:
+                self._engine_for(device).weights_resident(self._packed[1])
         return self._packed[1], self._packed[2]
 
     def _engine_for(self, device) -> Engine:

@@ -143,6 +143,13 @@ typedef struct {
   int32_t ignore_keypoint_regressor;      /* models/minkgl.py:296-299 */
 } egn_net;
 
+/* Keep the weight blob resident in L2 across forwards: reserves a persisting-L2 carve-out
+ * (cudaLimitPersistingL2CacheSize, clamped to the device maximum) and makes egn_forward tag accesses to
+ * [weights, weights+bytes) as persisting on its streams (cudaStreamAttributeAccessPolicyWindow).  The 37 MB of
+ * fp32 + bf16 kernel images are re-read by every CTA of every layer of every batch; the ~1 GB of activations that
+ * stream through the 126 MB L2 per batch would otherwise evict them.  bytes == 0 removes the window. */
+int egn_weights_resident(egn_ctx *ctx, const void *weights, size_t bytes);
+
 /* ---- whole forward ----------------------------------------------------------------------------------
  * Replaces: MinkGL.forward models/minkgl.py:267-315 (MinkTrunk.forward :136-153, MinkHead.forward :46-60,
  * ECABasicBlock.forward layers/eca_block.py:56-73, GeM.forward layers/pooling.py:82-86, the three
@@ -210,6 +217,8 @@ typedef struct {
 int egn_profile_enable(egn_ctx *ctx, int enable);
 int egn_profile_read(egn_ctx *ctx, egn_profile_entry *out, int capacity, int *n_out, int reset);
 int64_t egn_launch_count(egn_ctx *ctx);
+/* debug only (EGN_TRACE=1): clock64 timeline of CTA 0 of the last tensor-core convolution, 64 chunks x 8 stamps (host) */
+int egn_debug_trace(egn_ctx *ctx, long long *host_out);
 
 #ifdef __cplusplus
 }
