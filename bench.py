@@ -7,7 +7,9 @@ descriptors) - see the contract in DESIGN.md "Measurement".
 A step = one pass of the hot path over one batch of synthetic clouds (default: BASELINE config 2, batch=16
 KITTI-64-beam-shaped clouds, 0.10 m voxels, per GPU: weak scaling).
   value : clouds/s with the voxelised batch already resident in HBM (egn_coords_build + egn_forward + top-256
-          keypoint selection), device-timed with CUDA events per step, L2 flushed between steps, max over ranks.
+          keypoint selection); EXACTLY K steps between two synchronisations, device time by CUDA events around the
+          region, K steps round-robin over --streams (default 3) engine contexts, 256 MiB L2 flush before every step
+          (inside the timed region), max over ranks.
   e2e   : same metric through the public API (model.forward_points) from pinned HOST point clouds: H2D of the raw
           points, fused GPU quantisation + pyramid, forward, keypoint selection, D2H of global descriptors + top-256
           keypoints and their descriptors - all inside the timed region (wall clock, sync on both sides; the H2D
@@ -150,6 +152,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=list(synth.CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="clouds per GPU per step (default: the config's batch)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=3, help="concurrent CUDA streams / engine contexts per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-class table (JSON) here")
     args = ap.parse_args()
@@ -186,12 +189,37 @@ def main():
     gathered = torch.empty((world * batch, 256), device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # 256 MiB > 126 MB L2
 
+    S = max(1, args.streams)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+
     def step_device():
         p = model.forward_packed({"coords": bcoords, "features": feats})
         idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK)
         if world > 1:
             dist.all_gather_into_tensor(gathered, p["global"])
         return p, idx
+
+    def run_device(n_steps, do_flush=True):
+        """n_steps steps round-robin over S streams (one engine context each): a batch's small upper pyramid levels
+        overlap the other batch's large levels.  The L2 flush of every step is INSIDE the timed region."""
+        cur = torch.cuda.current_stream()
+        start = torch.cuda.Event(enable_timing=True)
+        end = torch.cuda.Event(enable_timing=True)
+        start.record(cur)
+        for st in streams:
+            st.wait_event(start)
+        for i in range(n_steps):
+            with torch.cuda.stream(streams[i % S]):
+                if do_flush:
+                    flush.zero_()
+                step_device()
+        for st in streams:
+            e = torch.cuda.Event()
+            e.record(st)
+            cur.wait_event(e)
+        end.record(cur)
+        torch.cuda.synchronize()
+        return start.elapsed_time(end)
 
     # ---- host-resident raw clouds (the `e2e` arm): pinned host points -> H2D -> fused quantise+pyramid -> forward ->
     #      top-k -> D2H of global descriptors, top-256 keypoints and their descriptors.  Two device slots: the H2D of step
@@ -200,15 +228,16 @@ def main():
     starts = np.cumsum([0] + [t.shape[0] for t in host_pts]).astype(np.int32)
     off_host = torch.from_numpy(starts).pin_memory()
     h2d_bytes = sum(t.numel() * 4 for t in host_pts) + off_host.numel() * 4
-    dev_pts = [torch.empty((int(starts[-1]), 3), device=dev) for _ in range(2)]
-    dev_off = [torch.empty((batch + 1,), dtype=torch.int32, device=dev) for _ in range(2)]
-    out_g = [torch.empty((batch, 256), dtype=torch.float32).pin_memory() for _ in range(2)]
-    out_kp = [torch.empty((batch, TOPK, 3), dtype=torch.float32).pin_memory() for _ in range(2)]
-    out_ds = [torch.empty((batch, TOPK, 128), dtype=torch.float32).pin_memory() for _ in range(2)]
+    NS = max(2, S)                                        # device slots: H2D of later steps overlaps compute of earlier ones
+    dev_pts = [torch.empty((int(starts[-1]), 3), device=dev) for _ in range(NS)]
+    dev_off = [torch.empty((batch + 1,), dtype=torch.int32, device=dev) for _ in range(NS)]
+    out_g = [torch.empty((batch, 256), dtype=torch.float32).pin_memory() for _ in range(NS)]
+    out_kp = [torch.empty((batch, TOPK, 3), dtype=torch.float32).pin_memory() for _ in range(NS)]
+    out_ds = [torch.empty((batch, TOPK, 128), dtype=torch.float32).pin_memory() for _ in range(NS)]
     d2h_bytes = (out_g[0].numel() + out_kp[0].numel() + out_ds[0].numel()) * 4
     copy_stream = torch.cuda.Stream(device=dev)
-    ev_h2d = [torch.cuda.Event() for _ in range(2)]
-    ev_done = [torch.cuda.Event() for _ in range(2)]
+    ev_h2d = [torch.cuda.Event() for _ in range(NS)]
+    ev_done = [torch.cuda.Event() for _ in range(NS)]
     for e in ev_done:
         e.record()
 
@@ -221,24 +250,26 @@ def main():
             ev_h2d[slot].record(copy_stream)
 
     def compute_e2e(slot):
-        cur = torch.cuda.current_stream()
-        cur.wait_event(ev_h2d[slot])
-        p = model.forward_points(dev_pts[slot], dev_off[slot])
-        idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK).long()
-        rows = (idx.clamp_min(0) + p["local_offsets"][:-1].long()[:, None])
-        out_g[slot].copy_(p["global"], non_blocking=True)
-        out_kp[slot].copy_(p["keypoints"][rows], non_blocking=True)
-        out_ds[slot].copy_(p["descriptors"][rows], non_blocking=True)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, p["global"])
-        ev_done[slot].record(cur)
+        with torch.cuda.stream(streams[slot % S]):
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev_h2d[slot])
+            p = model.forward_points(dev_pts[slot], dev_off[slot])
+            idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK).long()
+            rows = (idx.clamp_min(0) + p["local_offsets"][:-1].long()[:, None])
+            out_g[slot].copy_(p["global"], non_blocking=True)
+            out_kp[slot].copy_(p["keypoints"][rows], non_blocking=True)
+            out_ds[slot].copy_(p["descriptors"][rows], non_blocking=True)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, p["global"])
+            ev_done[slot].record(cur)
 
     def run_e2e(n_steps):
-        enqueue_h2d(0)
+        for i in range(min(NS - 1, n_steps)):
+            enqueue_h2d(i % NS)
         for i in range(n_steps):
-            if i + 1 < n_steps:
-                enqueue_h2d((i + 1) % 2)
-            compute_e2e(i % 2)
+            if i + NS - 1 < n_steps:
+                enqueue_h2d((i + NS - 1) % NS)
+            compute_e2e(i % NS)
         torch.cuda.synchronize()
 
     def barrier():
@@ -246,29 +277,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    eng = None
-    for _ in range(W):
-        step_device()
-    eng = model._engine
+    run_device(max(W, S))
     barrier()
 
-    # ---- timed region: K steps, CUDA events per step, L2 flush between steps ----
+    # ---- timed region: EXACTLY K steps between two synchronisations; device time by CUDA events around the region ----
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = eng.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    engines = list(model._engines.values())
+    launches0 = sum(e.launch_count() for e in engines)
     barrier()
     t_wall0 = time.perf_counter()
-    for a, b in ev:
-        flush.zero_()
-        a.record()
-        step_device()
-        b.record()
+    total_ms = run_device(K)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = (eng.launch_count() - launches0) / K
-    dev_ms = [a.elapsed_time(b) for a, b in ev]
-    ms_step = float(np.sum(dev_ms) / K)
+    launches = (sum(e.launch_count() for e in engines) - launches0) / K + 1        # + the top-k kernel of every step
+    ms_step = float(total_ms / K)
+    eng = model._engine
 
     # ---- e2e arm ----
     run_e2e(3)
@@ -280,6 +304,8 @@ def main():
     clocks = sampler.stop()
 
     # ---- per-kernel-class profile (separate pass so the event brackets do not perturb the timed region) ----
+    step_device()                                   # engine context of the default stream
+    eng = model._engine
     eng.profile(True)
     for _ in range(min(K, 10)):
         flush.zero_()
@@ -322,7 +348,8 @@ def main():
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": f"synthetic ({wdesc})",
                 "config": {"workload": f"{args.config}: {desc}", "clouds_per_gpu": batch, "voxels_per_gpu_step": voxels,
-                           "level_rows": eng.info.n_rows[:8], "voxel_m": voxel, "topk": TOPK, "l2_flush_between_steps": True,
+                           "level_rows": eng.info.n_rows[:8], "voxel_m": voxel, "topk": TOPK, "l2_flush_between_steps": True, "l2_flush_inside_timed_region": True, "streams_per_gpu": S,
+                           "weights_l2_persisting": True,
                            "parallelism": f"dp{world} over clouds" + (", 1 NCCL all-gather of global descriptors" if world > 1 else "")},
                 "clocks": clocks,
                 "e2e": {"value": world * batch / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,

@@ -260,6 +260,7 @@ class MinkGL(nn.Module):
         self.ignore_keypoint_regressor = False
         self.l2_resident_weights = True   # keep the 37 MB weight blob in a persisting L2 window (egn_weights_resident)
         self._engine: Optional[Engine] = None
+        self._engines: Dict = {}
         self._packed = None       # (signature, blob on device, Net)
         self.last: Dict = {}      # extras of the last forward: local coordinates, batch offsets, level sizes
 
@@ -278,13 +279,21 @@ class MinkGL(nn.Module):
                                      bn_eps=self.trunk.bn["0"].bn.eps)
             self._packed = (sig, blob.to(device), net)
             if self.l2_resident_weights:
-                self._engine_for(device).weights_resident(self._packed[1])
+                for eng in self._engines.values():
+                    eng.weights_resident(self._packed[1])
         return self._packed[1], self._packed[2]
 
     def _engine_for(self, device) -> Engine:
-        if self._engine is None or self._engine.device != device:
-            self._engine = Engine(device)
-        return self._engine
+        """One engine context (coordinate manager + scratch arenas) per (device, CUDA stream): running the model under
+        different ``torch.cuda.stream`` contexts gives independent contexts whose forwards overlap on the GPU."""
+        key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = self._engines[key] = Engine(device)
+            if self._packed is not None and self.l2_resident_weights:
+                eng.weights_resident(self._packed[1])
+        self._engine = eng                                    # the engine of the most recent call (taps, counters)
+        return eng
 
     # -- fused path ------------------------------------------------------------------------------------------
     @torch.no_grad()
