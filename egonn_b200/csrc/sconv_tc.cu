@@ -190,7 +190,7 @@ struct Cfg {
   static constexpr int kPrefetch = 1;                               // chunks gathered ahead in registers
   static constexpr int kThreads = (kProducerWarps + 2) * 32;
   static constexpr int kBBytes = 2 * COUT * 128;                    // hi + lo image of one weight chunk
-  static constexpr int kBSlots = COUT == 128 ? 3 : (CIN == 128 ? (COUT == 64 ? 6 : 8) : (COUT == 32 ? 4 : 2));
+  static constexpr int kBSlots = kStages;                          // weight chunk i lives in slot i % kStages, same barrier as the A stage
   static constexpr int kABytesAll = kStages * 2 * kABytes;
   static constexpr int kSmemBytes = kABytesAll + kBSlots * kBBytes + kRows * 27 * 4 + 2 * COUT * 4 + 768;
 };
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], NPW);       // one arrive per gather warp
+      mbar_init(&full[s], NPW + 1);   // one arrive per gather warp + the TMA thread's arrive.expect_tx
       mbar_init(&empty[s], 1);        // one tcgen05.commit
     }
     for (int s = 0; s < kBSlots; ++s) {
@@ -411,13 +411,13 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
         const int j = s_list[i];
         const int sb = i % kBSlots;
         const uint32_t ph = (uint32_t)(i / kBSlots) & 1u;
-        mbar_wait(&bempty[sb], ph ^ 1u, a.hint_single);
-        mbar_arrive_expect_tx(&bfull[sb], (uint32_t)C::kBBytes);
+        mbar_wait(&empty[sb], ph ^ 1u, a.hint_single);
+        mbar_arrive_expect_tx(&full[sb], (uint32_t)C::kBBytes);
         // this CTA's COUT rows of the hi image and of the lo image of chunk j (contiguous when COUT == cout_total)
         const uint8_t *src = a.wpack + (size_t)j * 2 * a.cout_total * 128 + (size_t)col0 * 128;
         uint8_t *dst = btiles + sb * C::kBBytes;
-        bulk_g2s(dst, src, (uint32_t)(COUT * 128), &bfull[sb]);
-        bulk_g2s(dst + COUT * 128, src + (size_t)a.cout_total * 128, (uint32_t)(COUT * 128), &bfull[sb]);
+        bulk_g2s(dst, src, (uint32_t)(COUT * 128), &full[sb]);
+        bulk_g2s(dst + COUT * 128, src + (size_t)a.cout_total * 128, (uint32_t)(COUT * 128), &full[sb]);
       }
     }
   } else {
@@ -431,9 +431,8 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
       const int s = i % kStages, sb = i % kBSlots;
       const bool tr = a.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && i < 64 && lane == 0;
       if (tr) a.trace[i * 8 + 0] = clock64();
-      mbar_wait(&bfull[sb], (uint32_t)(i / kBSlots) & 1u, a.hint_single);
       if (tr) a.trace[i * 8 + 1] = clock64();
-      mbar_wait(&full[s], (uint32_t)(i / kStages) & 1u, a.hint_single);
+      mbar_wait(&full[s], (uint32_t)(i / kStages) & 1u, a.hint_single);   // gathered rows AND the weight chunk have landed
       if (tr) a.trace[i * 8 + 2] = clock64();
       tc_fence_after();
       const uint32_t sa = smem_u32(tiles + s * (2 * kABytes));
@@ -448,8 +447,7 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
           umma_f16(tmem_base, alo, bhi, idesc, 1u);
           umma_f16(tmem_base, ahi, blo, idesc, 1u);
         }
-        umma_commit(&empty[s]);          // A stage and B slot reusable once these MMAs have read them
-        umma_commit(&bempty[sb]);
+        umma_commit(&empty[s]);          // A stage and weight slot reusable once these MMAs have read them
       }
       __syncwarp();
       if (tr) a.trace[i * 8 + 4] = clock64();
