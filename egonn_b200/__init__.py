@@ -10,8 +10,9 @@ Everything that computes runs in hand-written sm_100a CUDA kernels behind the C 
 ``include/egonn_b200.h`` (``egonn_b200/csrc/libegonn_b200.so``).  There is no CPU fallback.
 """
 from .params import ModelParams  # noqa: F401
-from .models import model_factory, create_egonn_model, MinkGL, MinkTrunk, MinkHead, ECABasicBlock  # noqa: F401
+from .models import (model_factory, create_egonn_model, MinkGL, MinkTrunk, MinkHead, ECABasicBlock, MinkFPN,  # noqa: F401
+                     MinkLoc, MinkLoc3D)
 from .quantization import CartesianQuantizer, PolarQuantizer, batched_coordinates  # noqa: F401
-from .engine import Engine, topk_smallest  # noqa: F401
+from .engine import Engine, topk_smallest, knn_global  # noqa: F401
 
 __version__ = "0.1.0"

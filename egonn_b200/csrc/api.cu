@@ -277,6 +277,13 @@ int egn_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const flo
   return op_broadcast_mul(ctx, level, c, in, gate, out, (cudaStream_t)stream);
 }
 
+int egn_knn_l2(egn_ctx *ctx, const float *query, const float *map, int n_query, int n_map, int dim, int k, int32_t *idx_out,
+               float *dist_out, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return op_knn_l2(ctx, query, map, n_query, n_map, dim, k, idx_out, dist_out, (cudaStream_t)stream);
+}
+
 int egn_profile_enable(egn_ctx *ctx, int enable) {
   EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
   ctx->prof.on = enable != 0;

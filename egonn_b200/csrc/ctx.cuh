@@ -106,6 +106,8 @@ int op_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int 
 int op_global_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, float p, float eps, float *out,
                    cudaStream_t s);
 int op_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const float *g, float *out, cudaStream_t s);
+int op_knn_l2(egn_ctx *ctx, const float *query, const float *map, int Q, int M, int D, int k, int32_t *idx_out, float *dist_out,
+              cudaStream_t s);
 int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out, cudaStream_t s);
 // sconv_tc.cu
 bool sconv_tc_supported(int ksize, int transposed, int cin, int cout);

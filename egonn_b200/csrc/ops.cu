@@ -683,6 +683,42 @@ int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, in
   return EGN_OK;
 }
 
+// ---- global-descriptor retrieval (eval/evaluate.py:173-176) ------------------------------------------------
+// embed_dist = ||map - query||_2 computed on the difference (like np.linalg.norm(map - q, axis=1)), one warp per
+// (query, map row); nn = the k smallest per query by the same radix select + bitonic sort as the keypoint top-k.
+__global__ void k_l2_dist(const float *__restrict__ query, const float *__restrict__ map, int Q, int M, int D, float *__restrict__ dist) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5, total = (int64_t)Q * M;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += warps) {
+    const int q = (int)(w / M), m = (int)(w % M);
+    const float *a = query + (size_t)q * D, *b = map + (size_t)m * D;
+    float ss = 0.f;
+    for (int d = lane; d < D; d += 32) { const float t = b[d] - a[d]; ss = fmaf(t, t, ss); }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    if (lane == 0) dist[w] = sqrtf(ss);
+  }
+}
+__global__ void k_row_offsets(int *__restrict__ off, int Q, int M) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= Q; i += gridDim.x * blockDim.x) off[i] = i * M;
+}
+
+int op_knn_l2(egn_ctx *ctx, const float *query, const float *map, int Q, int M, int D, int k, int32_t *idx_out, float *dist_out,
+              cudaStream_t s) {
+  EGN_CHECK(ctx && query && map && idx_out && dist_out, EGN_ERR_INVALID, "knn: null argument");
+  EGN_CHECK(Q >= 1 && M >= 1 && D >= 1 && k >= 1 && k <= kTopkMaxK && (int64_t)Q * M < ((int64_t)1 << 31), EGN_ERR_INVALID,
+            "knn: bad sizes (Q=%d M=%d D=%d k=%d)", Q, M, D, k);
+  EGN_TRY(ctx->scratch.reserve(pad256((size_t)(Q + 1) * 4) + 4096, s));
+  int *off = (int *)ctx->scratch.take((size_t)(Q + 1) * 4);
+  EGN_CHECK(off != nullptr, EGN_ERR_STATE, "scratch arena exhausted");
+  EGN_LAUNCH(ctx, "retrieval_l2_dist", (double)Q * M * (D * 4.0 + 4), 3.0 * Q * M * D, s,
+             k_l2_dist<<<grid_for((int64_t)Q * M * 32, 256, 16), 256, 0, s>>>(query, map, Q, M, D, dist_out));
+  k_row_offsets<<<(Q + 256) / 256, 256, 0, s>>>(off, Q, M);
+  EGN_LAUNCH(ctx, "retrieval_topk", (double)Q * M * 4, 0, s, k_topk_smallest<<<Q, kTopkThreads, 0, s>>>(dist_out, off, k, idx_out));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+
 // exported to forward.cu
 __global__ void k_fill_ones(float *__restrict__ out, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = 1.0f;

@@ -230,6 +230,29 @@ class Engine:
         return out
 
 
+_retrieval_engines = {}
+
+
+def knn_global(query: torch.Tensor, map_embeddings: torch.Tensor, k: int):
+    """Nearest neighbours of every query descriptor in the map set by Euclidean distance (eval/evaluate.py:173-176).
+    Returns (idx (Q,k) int64 map rows, ascending distance; dist (Q,k) f32).  CUDA tensors only."""
+    _need_cuda(query, "query")
+    _need_cuda(map_embeddings, "map_embeddings")
+    q = query.detach().to(torch.float32).contiguous()
+    m = map_embeddings.detach().to(torch.float32).contiguous()
+    assert q.dim() == 2 and m.dim() == 2 and q.shape[1] == m.shape[1]
+    key = q.device.index or 0
+    if key not in _retrieval_engines:
+        _retrieval_engines[key] = Engine(q.device)
+    eng = _retrieval_engines[key]
+    idx = torch.empty((q.shape[0], k), dtype=torch.int32, device=q.device)
+    dist = torch.empty((q.shape[0], m.shape[0]), dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        L.check(eng.lib.egn_knn_l2(eng._ctx, _ptr(q), _ptr(m), q.shape[0], m.shape[0], q.shape[1], k, _ptr(idx), _ptr(dist), _stream()))
+    idx = idx.long()
+    return idx, torch.gather(dist, 1, idx.clamp_min(0))
+
+
 def topk_smallest(sigma: torch.Tensor, offsets: torch.Tensor, k: int) -> torch.Tensor:
     """Per-cloud indices of the k smallest sigma, ascending (eval/evaluate.py:352-361); -1 padded."""
     _need_cuda(sigma, "sigma")

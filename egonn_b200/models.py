@@ -232,7 +232,45 @@ class DescriptorDecoder(nn.Module):
         return ME.MinkowskiFunctional.normalize(x) if self.normalize else x
 
 
-class MinkGL(nn.Module):
+class _EngineModel(nn.Module):
+    """Shared host plumbing of the engine-backed models: one engine context per (device, stream), weights packed
+    lazily and re-packed when a parameter / buffer changes."""
+
+    def _init_engine_state(self):
+        self.l2_resident_weights = True   # keep the weight blob in a persisting L2 window (egn_weights_resident)
+        self._engine: Optional[Engine] = None
+        self._engines: Dict = {}
+        self._packed = None               # (signature, blob on device, Net)
+
+    def _signature(self, device):
+        return (str(device), bool(getattr(self, "ignore_keypoint_regressor", False)),
+                tuple((id(p), p._version) for p in self.parameters()), tuple((id(b), b._version) for b in self.buffers()))
+
+    def _pack(self, device):
+        sig = self._signature(device)
+        if self._packed is None or self._packed[0] != sig:
+            sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
+            blob, net = self._pack_weights(sd)
+            self._packed = (sig, blob.to(device), net)
+            if self.l2_resident_weights:
+                for eng in self._engines.values():
+                    eng.weights_resident(self._packed[1])
+        return self._packed[1], self._packed[2]
+
+    def _engine_for(self, device) -> Engine:
+        """One engine context (coordinate manager + scratch arenas) per (device, CUDA stream): running the model under
+        different ``torch.cuda.stream`` contexts gives independent contexts whose forwards overlap on the GPU."""
+        key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = self._engines[key] = Engine(device)
+            if self._packed is not None and self.l2_resident_weights:
+                eng.weights_resident(self._packed[1])
+        self._engine = eng                                    # the engine of the most recent call (taps, counters)
+        return eng
+
+
+class MinkGL(_EngineModel):
     """models/minkgl.py:228-315, executed by the CUDA engine."""
 
     def __init__(self, trunk: MinkTrunk, local_head: MinkHead = None, local_descriptor_size: int = None,
@@ -258,42 +296,15 @@ class MinkGL(nn.Module):
             self.local_descriptor_decoder = DescriptorDecoder(c, local_descriptor_size, normalize=local_normalize)
         self.quantizer = quantizer
         self.ignore_keypoint_regressor = False
-        self.l2_resident_weights = True   # keep the 37 MB weight blob in a persisting L2 window (egn_weights_resident)
-        self._engine: Optional[Engine] = None
-        self._engines: Dict = {}
-        self._packed = None       # (signature, blob on device, Net)
+        self._init_engine_state()
         self.last: Dict = {}      # extras of the last forward: local coordinates, batch offsets, level sizes
 
     # -- weights -> engine ------------------------------------------------------------------------------------
-    def _signature(self, device):
-        return (str(device), bool(self.ignore_keypoint_regressor),
-                tuple((id(p), p._version) for p in self.parameters()), tuple((id(b), b._version) for b in self.buffers()))
+    def _pack_weights(self, sd):
+        return W.pack_egonn(sd, self.quantizer.describe(), global_levels=self.global_head.in_levels,
+                            local_levels=self.local_head.in_levels if self.local_head is not None else (),
+                            ignore_keypoint_regressor=self.ignore_keypoint_regressor, bn_eps=self.trunk.bn["0"].bn.eps)
 
-    def _pack(self, device):
-        sig = self._signature(device)
-        if self._packed is None or self._packed[0] != sig:
-            sd = {k: v.detach().cpu() for k, v in self.state_dict().items()}
-            blob, net = W.pack_egonn(sd, self.quantizer.describe(), global_levels=self.global_head.in_levels,
-                                     local_levels=self.local_head.in_levels if self.local_head is not None else (),
-                                     ignore_keypoint_regressor=self.ignore_keypoint_regressor,
-                                     bn_eps=self.trunk.bn["0"].bn.eps)
-            self._packed = (sig, blob.to(device), net)
-            if self.l2_resident_weights:
-                for eng in self._engines.values():
-                    eng.weights_resident(self._packed[1])
-        return self._packed[1], self._packed[2]
-
-    def _engine_for(self, device) -> Engine:
-        """One engine context (coordinate manager + scratch arenas) per (device, CUDA stream): running the model under
-        different ``torch.cuda.stream`` contexts gives independent contexts whose forwards overlap on the GPU."""
-        key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream)
-        eng = self._engines.get(key)
-        if eng is None:
-            eng = self._engines[key] = Engine(device)
-            if self._packed is not None and self.l2_resident_weights:
-                eng.weights_resident(self._packed[1])
-        self._engine = eng                                    # the engine of the most recent call (taps, counters)
-        return eng
 
     # -- fused path ------------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -378,6 +389,139 @@ class MinkGL(nn.Module):
         print(f"Model class: {type(self).__name__}   # parameters: {n / 1000:.1f}k   (egonn_b200 CUDA engine)")
 
 
+# ---- models/minkfpn.py, models/minkloc.py, third_party/minkloc3d/minkloc.py ------------------------------------------
+class MinkFPN(nn.Module):
+    """Parameter tree of the reference's MinkFPN (models/minkfpn.py:9-93 on top of models/resnet.py:31-117): bottom-up
+    conv0 + n x (2x2x2 stride-2 conv, BN, block), top-down 1x1 laterals + transposed convolutions.  The module order
+    (convs, bn, blocks, tconvs, conv1x1, conv0, bn0) reproduces the reference's state_dict key order."""
+
+    def __init__(self, in_channels, out_channels, num_top_down=1, conv0_kernel_size=5, block=BasicBlock,
+                 layers=(1, 1, 1), planes=(32, 64, 64)):
+        super().__init__()
+        assert len(layers) == len(planes) and 1 <= len(layers) and 0 <= num_top_down <= len(layers)
+        assert all(n == 1 for n in layers), "the CUDA engine schedules one block per level"
+        self.num_bottom_up, self.num_top_down = len(layers), num_top_down
+        self.conv0_kernel_size, self.block, self.layers, self.planes = conv0_kernel_size, block, layers, planes
+        self.lateral_dim, self.init_dim = out_channels, planes[0]
+        self.convs, self.bn, self.blocks = nn.ModuleList(), nn.ModuleList(), nn.ModuleList()
+        self.tconvs, self.conv1x1 = nn.ModuleList(), nn.ModuleList()
+        self.inplanes = planes[0]
+        conv0 = ME.MinkowskiConvolution(in_channels, self.inplanes, kernel_size=conv0_kernel_size, dimension=3)
+        bn0 = ME.MinkowskiBatchNorm(self.inplanes)
+        for plane in planes:
+            self.convs.append(ME.MinkowskiConvolution(self.inplanes, self.inplanes, kernel_size=2, stride=2, dimension=3))
+            self.bn.append(ME.MinkowskiBatchNorm(self.inplanes))
+            self.blocks.append(self._make_layer(block, plane))
+        for i in range(num_top_down):
+            self.conv1x1.append(ME.MinkowskiConvolution(planes[-1 - i], out_channels, kernel_size=1, stride=1, dimension=3))
+            self.tconvs.append(ME.MinkowskiConvolutionTranspose(out_channels, out_channels, kernel_size=2, stride=2, dimension=3))
+        last = planes[-1 - num_top_down] if num_top_down < self.num_bottom_up else planes[0]
+        self.conv1x1.append(ME.MinkowskiConvolution(last, out_channels, kernel_size=1, stride=1, dimension=3))
+        self.conv0, self.bn0 = conv0, bn0
+        self.relu = ME.MinkowskiReLU(inplace=True)
+        for m in self.modules():                                      # models/resnet.py:72-79
+            if isinstance(m, ME.MinkowskiConvolution):
+                ME.utils.kaiming_normal_(m.kernel, mode="fan_out", nonlinearity="relu")
+            if isinstance(m, ME.MinkowskiBatchNorm):
+                nn.init.constant_(m.bn.weight, 1)
+                nn.init.constant_(m.bn.bias, 0)
+
+    def _make_layer(self, block, planes):
+        downsample = None
+        if self.inplanes != planes * block.expansion:
+            downsample = nn.Sequential(
+                ME.MinkowskiConvolution(self.inplanes, planes * block.expansion, kernel_size=1, stride=1, dimension=3),
+                ME.MinkowskiBatchNorm(planes * block.expansion))
+        layer = nn.Sequential(block(self.inplanes, planes, stride=1, dilation=1, downsample=downsample, dimension=3))
+        self.inplanes = planes * block.expansion
+        return layer
+
+    def forward(self, x):                                             # layer-wise operator walk (models/minkfpn.py:65-93)
+        maps = []
+        x = self.relu(self.bn0(self.conv0(x)))
+        if self.num_top_down == self.num_bottom_up:
+            maps.append(x)
+        for ndx, (conv, bn, block) in enumerate(zip(self.convs, self.bn, self.blocks)):
+            x = block(self.relu(bn(conv(x))))
+            if self.num_bottom_up - 1 - self.num_top_down <= ndx < len(self.convs) - 1:
+                maps.append(x)
+        x = self.conv1x1[0](x)
+        for ndx, tconv in enumerate(self.tconvs):
+            x = tconv(x)
+            x = x + self.conv1x1[ndx + 1](maps[-ndx - 1])
+        return x
+
+
+class _GlobalOnlyModel(_EngineModel):
+    """MinkFPN backbone + global pooling, executed by the CUDA engine (models/minkloc.py:44-61)."""
+
+    def _finish_init(self, quantizer):
+        self.quantizer = quantizer
+        self._init_engine_state()
+
+    def _quant_desc(self):
+        return self.quantizer.describe() if self.quantizer is not None else {"coordinates": "cartesian", "step": 1.0}
+
+    @torch.no_grad()
+    def forward(self, batch, disable_local_head: bool = True):
+        assert disable_local_head, "this model has only the global head"
+        assert not self.training, "egonn_b200 runs inference only: call model.eval()"
+        coords, feats = batch["coords"], batch["features"]
+        if not coords.is_cuda or not feats.is_cuda:
+            raise RuntimeError("egonn_b200 has no CPU path: move batch['coords'] and batch['features'] to a CUDA device")
+        eng = self._engine_for(coords.device)
+        blob, net = self._pack(coords.device)
+        with torch.cuda.device(coords.device):
+            eng.build(coords)
+            out = eng.forward(net, blob, feats, want_global=True, want_local=False)
+        x = out["global"]
+        assert x.dim() == 2 and x.shape[1] == self.output_dim
+        return {"global": x}
+
+    @torch.no_grad()
+    def forward_layerwise(self, batch):
+        x = self.backbone(ME.SparseTensor(batch["features"], coordinates=batch["coords"]))
+        return {"global": self.pooling(x)}
+
+
+class MinkLoc(_GlobalOnlyModel):
+    """models/minkloc.py:13-61."""
+
+    def __init__(self, in_channels, feature_size, output_dim, planes, layers, num_top_down, conv0_kernel_size,
+                 block="BasicBlock", pooling_method="GeM", quantizer=None):
+        super().__init__()
+        blocks = {"BasicBlock": BasicBlock, "ECABasicBlock": ECABasicBlock}
+        if block not in blocks:
+            raise NotImplementedError("Unsupported network block: {}".format(block))
+        assert in_channels == 1
+        self.in_channels, self.feature_size, self.output_dim, self.block = in_channels, feature_size, output_dim, block
+        self.pooling_method = pooling_method
+        self.backbone = MinkFPN(in_channels=in_channels, out_channels=feature_size, num_top_down=num_top_down,
+                                conv0_kernel_size=conv0_kernel_size, block=blocks[block], layers=layers, planes=planes)
+        self.pooling = PoolingWrapper(pool_method=pooling_method, in_dim=feature_size, output_dim=output_dim)
+        self.pooled_feature_size = self.pooling.output_dim
+        self._finish_init(quantizer)
+
+    def _pack_weights(self, sd):
+        return W.pack_minkfpn(sd, self._quant_desc(), self.backbone.num_top_down, pool_method=self.pooling_method,
+                              pool_key="pooling.pooling.p", bn_eps=self.backbone.bn0.bn.eps)
+
+
+class MinkLoc3D(_GlobalOnlyModel):
+    """third_party/minkloc3d/minkloc.py:9-58 (MinkFPN 32/64/64, one top-down step, 256 channels, its own GeM)."""
+
+    def __init__(self, quantizer=None):
+        super().__init__()
+        self.feature_size = self.output_dim = 256
+        self.backbone = MinkFPN(in_channels=1, out_channels=self.feature_size, num_top_down=1, conv0_kernel_size=5,
+                                layers=[1, 1, 1], planes=[32, 64, 64])
+        self.pooling = GeM(input_dim=self.feature_size)
+        self._finish_init(quantizer)
+
+    def _pack_weights(self, sd):
+        return W.pack_minkfpn(sd, self._quant_desc(), 1, pool_method="GeM", pool_key="pooling.p", bn_eps=self.backbone.bn0.bn.eps)
+
+
 # ---- models/model_factory.py -----------------------------------------------------------------------------------
 def create_egonn_model(model_params):
     """models/model_factory.py:31-78."""
@@ -398,8 +542,15 @@ def create_egonn_model(model_params):
 
 
 def model_factory(model_params):
-    """models/model_factory.py:12-28.  'egonn' is scheduled by the CUDA engine; the MinkLoc / MinkLoc3D
-    configurations (MinkFPN + GeM) are the next row and not wired yet."""
+    """models/model_factory.py:12-28: 'MinkLoc', 'MinkLoc3D' and the 'egonn' family, all scheduled by the CUDA engine."""
+    in_channels = 1
+    if model_params.model == "MinkLoc":
+        return MinkLoc(in_channels=in_channels, feature_size=model_params.feature_size, output_dim=model_params.output_dim,
+                       planes=model_params.planes, layers=model_params.layers, num_top_down=model_params.num_top_down,
+                       conv0_kernel_size=model_params.conv0_kernel_size, block=model_params.block,
+                       pooling_method=model_params.pooling, quantizer=model_params.quantizer)
+    if model_params.model == "MinkLoc3D":
+        return MinkLoc3D(quantizer=model_params.quantizer)
     if "egonn" in (model_params.model or ""):
         return create_egonn_model(model_params)
     raise NotImplementedError("Model not implemented: {}".format(model_params.model))

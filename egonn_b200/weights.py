@@ -140,3 +140,56 @@ def pack_egonn(sd: Dict[str, torch.Tensor], quantizer_desc: dict, global_levels=
         net.quant_step[i] = float(step[i])
     net.ignore_keypoint_regressor = int(ignore_keypoint_regressor)
     return blob.tensor(), net
+
+
+def pack_minkfpn(sd: Dict[str, torch.Tensor], quantizer_desc: dict, num_top_down: int, pool_method: str = "GeM",
+                 backbone: str = "backbone", pool_key: Optional[str] = None, bn_eps: float = 1e-5):
+    """state_dict of models/minkloc.py:MinkLoc / third_party/minkloc3d/minkloc.py:MinkLoc3D (MinkFPN backbone,
+    models/minkfpn.py:9-93, + global pooling) -> (blob cpu f32, Net).  MinkFPN numbers its ModuleLists from 0:
+    convs[i]/bn[i]/blocks[i] build level i+1; conv1x1[0] sits on the top level T, conv1x1[j] on level T-j,
+    tconvs[j] maps level T-j -> T-j-1 (models/minkfpn.py:48-63,84-91)."""
+    blob = _Blob()
+    net = L.Net()
+    b = backbone
+    n_levels = 0
+    while f"{b}.convs.{n_levels}.kernel" in sd:
+        n_levels += 1
+    assert 1 <= n_levels < L.EGN_MAX_LEVELS and 0 <= num_top_down <= n_levels
+    net.n_levels = n_levels
+    k0 = sd[f"{b}.conv0.kernel"]
+    net.conv0_ksize = int(round(k0.shape[0] ** (1.0 / 3.0)))
+    net.conv0 = _conv(blob, k0, _bn_fold(sd, f"{b}.bn0.bn", bn_eps))
+    for lv in range(1, n_levels + 1):
+        i = lv - 1
+        net.down[lv] = _conv(blob, sd[f"{b}.convs.{i}.kernel"], _bn_fold(sd, f"{b}.bn.{i}.bn", bn_eps))
+        p = f"{b}.blocks.{i}.0"
+        assert f"{b}.blocks.{i}.1.conv1.kernel" not in sd, "more than one block per level is not supported yet"
+        net.conv1[lv] = _conv(blob, sd[p + ".conv1.kernel"], _bn_fold(sd, p + ".norm1.bn", bn_eps))
+        net.conv2[lv] = _conv(blob, sd[p + ".conv2.kernel"], _bn_fold(sd, p + ".norm2.bn", bn_eps))
+        if p + ".downsample.0.kernel" in sd:
+            net.res[lv] = _conv(blob, sd[p + ".downsample.0.kernel"], _bn_fold(sd, p + ".downsample.1.bn", bn_eps))
+        if p + ".eca.conv.weight" in sd:
+            w = sd[p + ".eca.conv.weight"].reshape(-1)
+            net.eca_k[lv], net.eca_w[lv] = w.numel(), blob.add(w)
+    top = n_levels
+    levels = list(range(top - num_top_down, top + 1))
+    h = L.Head()
+    h.n_levels = len(levels)
+    for i, lv in enumerate(levels):
+        h.levels[i] = lv
+    h.out_channels = sd[f"{b}.conv1x1.0.kernel"].shape[-1]
+    for j in range(num_top_down + 1):
+        h.conv1x1[top - j] = _conv(blob, sd[f"{b}.conv1x1.{j}.kernel"])
+    for j in range(num_top_down):
+        h.tconv[top - j] = _conv(blob, sd[f"{b}.tconvs.{j}.kernel"])
+    net.global_head = h
+    net.pool_method = {"GeM": 0, "SPoC": 1, "MAC": 2}[pool_method]
+    net.gem_p, net.gem_eps = 3.0, 1e-6
+    if pool_method == "GeM":
+        net.gem_p = float(sd[pool_key or "pooling.pooling.p"].reshape(-1)[0])
+    net.polar = 1 if quantizer_desc["coordinates"] == "polar" else 0
+    step = quantizer_desc["step"]
+    step = list(step) if isinstance(step, (list, tuple)) else [step, step, step]
+    for i in range(3):
+        net.quant_step[i] = float(step[i])
+    return blob.tensor(), net

@@ -201,6 +201,13 @@ int egn_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const flo
 int egn_topk_smallest(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out,
                       egn_stream_t stream);
 
+/* Replaces: the global-descriptor nearest-neighbour search of eval/evaluate.py:173-176
+ * (embed_dist = np.linalg.norm(map_embeddings - query_embedding, axis=1); nn_ndx = np.argsort(embed_dist)[:k]).
+ * query (n_query, dim), map (n_map, dim) f32; idx_out (n_query, k) int32 map rows by ascending distance (ties: lower
+ * row first, -1 padding if n_map < k); dist_out (n_query, n_map) f32 receives every distance (caller-owned scratch). */
+int egn_knn_l2(egn_ctx *ctx, const float *query, const float *map, int n_query, int n_map, int dim, int k, int32_t *idx_out,
+               float *dist_out, egn_stream_t stream);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------------
  * egn_profile_enable(ctx, 1): every kernel class launched by this context is bracketed by CUDA events on its
  * stream and the pair counts needed for the algorithmic-byte model are computed at coords_build.

@@ -189,3 +189,47 @@ def forward(sd: Dict[str, torch.Tensor], coords, feats: torch.Tensor, quant: dic
         fe["local_map"] = xl[ot]
         out["features"] = fe
     return out
+
+
+@torch.no_grad()
+def forward_minkloc(sd: Dict[str, torch.Tensor], coords, feats: torch.Tensor, num_top_down: int = 1,
+                    pool_method: str = "GeM", pool_key: str = "pooling.p", acc64: bool = False):
+    """MinkLoc.forward / MinkLoc3D.forward (models/minkloc.py:44-61, third_party/minkloc3d/minkloc.py:19-31) with the
+    MinkFPN backbone (models/minkfpn.py:65-93).  Returns {'global': (B,C), 'map': (coords, F) of the FPN output}."""
+    c = coords.detach().cpu().numpy() if isinstance(coords, torch.Tensor) else np.asarray(coords)
+    cm = me_ops.CoordinateManager(c)
+    nb = cm.n_batches
+    b = "backbone"
+    n_levels = 0
+    while f"{b}.convs.{n_levels}.kernel" in sd:
+        n_levels += 1
+    k0 = sd[f"{b}.conv0.kernel"]
+    x, _ = me_ops.convolution(cm, feats.float(), 1, k0, int(round(k0.shape[0] ** (1 / 3))), acc64=acc64)
+    x = torch.relu(_bn(sd, f"{b}.bn0", x))
+    maps = []
+    if num_top_down == n_levels:
+        maps.append((1, x))
+    stride = 1
+    for ndx in range(n_levels):
+        x, stride = me_ops.convolution(cm, x, stride, sd[f"{b}.convs.{ndx}.kernel"], 2, stride=2, acc64=acc64)
+        x = torch.relu(_bn(sd, f"{b}.bn.{ndx}", x))
+        has_eca = f"{b}.blocks.{ndx}.0.eca.conv.weight" in sd
+        x = eca_basic_block(sd, f"{b}.blocks.{ndx}.0", cm, x, stride, nb, acc64=acc64, eca=has_eca)
+        if n_levels - 1 - num_top_down <= ndx < n_levels - 1:
+            maps.append((stride, x))
+    x, _ = me_ops.convolution(cm, x, stride, sd[f"{b}.conv1x1.0.kernel"], 1, acc64=acc64)
+    for ndx in range(num_top_down):
+        x, stride = me_ops.convolution_transpose(cm, x, stride, sd[f"{b}.tconvs.{ndx}.kernel"], acc64=acc64)
+        ms, mf = maps[-ndx - 1]
+        assert ms == stride
+        lat, _ = me_ops.convolution(cm, mf, stride, sd[f"{b}.conv1x1.{ndx + 1}.kernel"], 1, acc64=acc64)
+        x = x + lat
+    cc = cm.coords(stride)
+    if pool_method == "GeM":
+        g = gem(x, cc, sd[pool_key], nb)
+    elif pool_method == "SPoC":
+        g = me_ops.global_avg_pool(x, cc, nb)
+    else:
+        g = me_ops.global_max_pool(x, cc, nb)
+    order = me_ops.canonical_order(cc)
+    return {"global": g, "map": (cc[order], x[torch.from_numpy(order)])}

@@ -344,3 +344,19 @@ def test_fused_points_ingest_matches_staged_path(case, cuda, weights):
     assert torch.equal(a["local_coords"], b["local_coords"]) and torch.equal(a["local_offsets"], b["local_offsets"])
     for k in ("global", "descriptors", "keypoints", "sigma"):
         assert_close_rel(a[k], b[k], 1e-6, k)
+
+
+def test_global_descriptor_retrieval_matches_numpy(cuda):
+    """egn_knn_l2 == np.argsort(np.linalg.norm(map - q, axis=1))[:k] (eval/evaluate.py:173-176)."""
+    import egonn_b200 as E
+    rng = np.random.default_rng(0)
+    m = rng.normal(size=(3000, 256)).astype(np.float32)
+    q = np.concatenate([m[[5, 17]] + 1e-3, rng.normal(size=(30, 256)).astype(np.float32)])
+    idx, dist = E.knn_global(torch.from_numpy(q).to(cuda), torch.from_numpy(m).to(cuda), 20)
+    for i in range(q.shape[0]):
+        d = np.linalg.norm(m - q[i], axis=1)
+        exp = np.argsort(d, kind="stable")[:20]
+        got = idx[i].cpu().numpy()
+        assert np.array_equal(got, exp) or np.allclose(d[got], d[exp], rtol=1e-6)
+        np.testing.assert_allclose(dist[i].cpu().numpy(), d[exp], rtol=1e-5)
+    assert idx[0, 0] == 5 and idx[1, 0] == 17
