@@ -1,0 +1,324 @@
+// Tensor-core sparse convolution, second generation: the gathered A operand lives in TENSOR MEMORY, not shared memory.
+//
+//   out[o, :] = epilogue( sum_k  in[nbr(o,k), :] @ W[k] )          (MinkowskiConvolution forward)
+//
+// Why: in k_sconv_tc (sconv_tc.cu) every 64-element chunk of the gathered operand is written to shared memory as
+// two bf16 images (32 KB of STS) and then read three times by tcgen05.mma (hi*hi, lo*hi, hi*lo: 48 KB) - the
+// shared-memory port and the instructions that feed it, not HBM and not the tensor pipe, bound the kernel
+// (profiles/r01_tc_kernel_stalls.md).  tcgen05.mma can take A from tensor memory ("TS" form), and tcgen05.st writes
+// registers straight into it, so here
+//   * producers : gather fp32 rows with 16-byte loads in the tcgen05.st.16x256b fragment layout (4 threads per row,
+//                 8 rows + 8 rows per warp instruction), split into bf16 hi/lo in registers, tcgen05.st both images
+//                 into a TMEM stage (64 columns: 32 hi + 32 lo).  No shared-memory traffic for A at all.
+//                 A warp may only touch its own TMEM lane quarter, so a GROUP of 4 warps builds one chunk
+//                 (warp q -> rows 32q..32q+31); the 2 (or 4) groups of a CTA work on alternate chunks.
+//   * weights   : unchanged - pre-swizzled bf16 hi/lo images, one cp.async.bulk (TMA) pair per chunk into a ring.
+//   * MMA       : per chunk 4 K-steps x {hi*hi, lo*hi, hi*lo}, A = TMEM columns, B = shared-memory descriptor,
+//                 FP32 accumulators in TMEM columns [0, COUT); tcgen05.commit frees the stage.
+//   * epilogue  : tcgen05.ld -> folded BatchNorm scale/shift (+ReLU, +accumulate) -> the output row, written once.
+// TMEM plan: COUT == 128: 1 CTA/SM, 512 columns = 128 accumulator + 6 stages x 64; otherwise 2 CTAs/SM, 256 columns
+// each = 64 accumulator + 3 stages x 64.  Same numerics as k_sconv_tc (bf16x3 split, FP32 accumulation).
+#include "ctx.cuh"
+#include "tc_ptx.cuh"
+
+namespace egn {
+
+namespace ts {
+
+using namespace tcx;
+
+template <int CIN, int COUT>
+struct Cfg {
+  static constexpr bool kBig = COUT == 128;
+  static constexpr int kGroups = kBig ? 4 : 2;             // producer groups; one warp per TMEM lane quarter in each
+  static constexpr int kProducerWarps = 4 * kGroups;
+  static constexpr int kStages = kBig ? 6 : 3;
+  static constexpr int kCtasPerSm = kBig ? 1 : 2;
+  static constexpr int kTmemCols = kBig ? 512 : 256;
+  static constexpr int kAccCols = kBig ? 128 : 64;         // A stages start here; accumulator = columns [0, COUT)
+  static constexpr int kThreads = (kProducerWarps + 2) * 32;
+  static constexpr int kBBytes = 2 * COUT * 128;           // hi + lo image of one weight chunk
+  static constexpr int kSmemBytes = kStages * kBBytes + kRows * 27 * 4 + 2 * COUT * 4 + 1024;
+};
+
+template <int CIN, int COUT, int KOFF>
+__global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCtasPerSm) k_sconv_ts(Args a) {
+  using C = Cfg<CIN, COUT>;
+  constexpr int kStages = C::kStages, NG = C::kGroups;
+  constexpr int NPW = C::kProducerWarps, NT = C::kThreads;
+  constexpr int NCH = (KOFF * CIN + kChunk - 1) / kChunk;         // chunks if nothing is skipped
+  constexpr int NBR_ITERS = (kRows * KOFF + NT - 1) / NT;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *btiles = smem;                                         // B ring: [kStages][hi | lo] (COUT*128 bytes each image)
+  int *s_nbr = (int *)(btiles + kStages * C::kBBytes);            // [kRows][KOFF]
+  float *s_scale = (float *)(s_nbr + kRows * 27);                 // [COUT]
+  float *s_shift = s_scale + COUT;                                // [COUT]
+  uint64_t *full = (uint64_t *)(s_shift + COUT);                  // [kStages]  A stage stored + weight chunk landed
+  uint64_t *empty = full + kStages;                               // [kStages]  stage consumed by the tensor core
+  uint64_t *accum = empty + kStages;                              // [1]
+  uint32_t *s_tmem = (uint32_t *)(accum + 1);
+  int *s_nlist = (int *)(s_tmem + 1);
+  uint32_t *s_present = (uint32_t *)(s_nlist + 1);                // [2] bit j: chunk j has at least one present row
+  int *s_list = (int *)(s_present + 2);                           // [NCH] compacted chunk ids
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * kRows;
+  const int col0 = blockIdx.y * COUT;     // N-split: this CTA computes output channels [col0, col0 + COUT)
+
+  if (tid == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 4 + 1);     // the 4 warps of the producing group + the TMA thread's arrive.expect_tx
+      mbar_init(&empty[s], 1);        // one tcgen05.commit
+    }
+    mbar_init(accum, 1);
+    fence_barrier_init();
+    s_present[0] = 0u;
+    s_present[1] = 0u;
+  }
+  if (warp == NPW + 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)C::kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int c = tid; c < COUT; c += NT) {
+    s_scale[c] = a.scale ? a.scale[col0 + c] : 1.f;
+    s_shift[c] = a.shift ? a.shift[col0 + c] : 0.f;
+  }
+  __syncthreads();                    // s_present zeroed before the atomics below
+  {
+    int src[NBR_ITERS];
+#pragma unroll
+    for (int it = 0; it < NBR_ITERS; ++it) {
+      const int t = tid + it * NT;
+      const int r = t / KOFF, k = t - r * KOFF, row = row0 + r;
+      src[it] = -1;
+      if (t < kRows * KOFF && row < a.n_out) {
+        if (a.mode == 0) src[it] = row;
+        else if (a.mode == 1) src[it] = __ldg(a.nbr + (int64_t)row0 * 27 + t);
+        else if (a.mode == 2) {
+          const uint32_t m = __ldg(a.cmask + row);
+          if ((m >> k) & 1u) src[it] = __ldg(a.cstart + row) + __popc(m & ((1u << k) - 1u));
+        } else {
+          if ((int)(__ldg(a.keys + row) & 7ull) == k) src[it] = __ldg(a.up + row);
+        }
+      }
+    }
+    uint32_t m0 = 0u, m1 = 0u;
+#pragma unroll
+    for (int it = 0; it < NBR_ITERS; ++it) {
+      const int t = tid + it * NT;
+      if (t < kRows * KOFF) {
+        s_nbr[t] = src[it];
+        if (src[it] >= 0) {
+          const int k = t % KOFF;
+          const int j = CIN == 128 ? 2 * k : (CIN == 64 ? k : (k >> 1));
+          const uint32_t bits = CIN == 128 ? 3u : 1u;
+          if (j < 32) m0 |= bits << j; else m1 |= bits << (j - 32);
+        }
+      }
+    }
+    m0 = __reduce_or_sync(0xffffffffu, m0);
+    m1 = __reduce_or_sync(0xffffffffu, m1);
+    if (lane == 0) {
+      if (m0) atomicOr(&s_present[0], m0);
+      if (m1) atomicOr(&s_present[1], m1);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const int j_lo = (int)(((int64_t)NCH * blockIdx.z) / a.ksplit), j_hi = (int)(((int64_t)NCH * (blockIdx.z + 1)) / a.ksplit);
+    int n = 0;
+    for (int j = j_lo; j < j_hi; ++j)
+      if ((s_present[j >> 5] >> (j & 31)) & 1u) s_list[n++] = j;
+    *s_nlist = n;
+  }
+  __syncthreads();
+  const int nlist = *s_nlist;
+  const uint32_t tmem_base = *s_tmem;
+
+  if (warp < NPW) {
+    // ===================== A producers: gather -> bf16 hi/lo split -> tcgen05.st =====================
+    // warp = 4*g + q: group g builds chunks g, g+NG, ...; this warp owns TMEM lanes 32q..32q+31 (= tile rows).
+    // lane = 4*i8 + j4: per 16-lane half hf the thread feeds rows 32q + 16hf + i8 (+8), K positions 16m + 4*j4 .. +3.
+    const int q = warp & 3, g = warp >> 2, i8 = lane >> 2, j4 = lane & 3;
+    const int *nb_base = s_nbr + (32 * q + i8) * KOFF;
+    for (int i = g; i < nlist; i += NG) {
+      const int jc = s_list[i];
+      const int s = i % kStages;
+      const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+      float4 v[2][2][4];                                     // [half][row select][m]
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+        for (int rs = 0; rs < 2; ++rs) {
+          const int *nb = nb_base + (16 * hf + 8 * rs) * KOFF;
+          if (CIN == 32) {
+            const int k0 = 2 * jc, k1 = 2 * jc + 1;
+            const int s0 = nb[k0], s1 = k1 < KOFF ? nb[k1] : -1;
+            const float *p0 = a.in + (size_t)(s0 >= 0 ? s0 : 0) * CIN + 4 * j4;
+            const float *p1 = a.in + (size_t)(s1 >= 0 ? s1 : 0) * CIN + 4 * j4;
+            ldg4_pred(p0, s0 >= 0, v[hf][rs][0]);
+            ldg4_pred(p0 + 16, s0 >= 0, v[hf][rs][1]);
+            ldg4_pred(p1, s1 >= 0, v[hf][rs][2]);
+            ldg4_pred(p1 + 16, s1 >= 0, v[hf][rs][3]);
+          } else {
+            const int k = CIN == 64 ? jc : (jc >> 1);
+            const int s0 = nb[k];
+            const float *p0 = a.in + (size_t)(s0 >= 0 ? s0 : 0) * CIN + (CIN == 128 ? (jc & 1) * 64 : 0) + 4 * j4;
+#pragma unroll
+            for (int m = 0; m < 4; ++m) ldg4_pred(p0 + 16 * m, s0 >= 0, v[hf][rs][m]);
+          }
+        }
+      mbar_wait(&empty[s], ph ^ 1u, a.hint_producer);
+      tc_fence_after();
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+#pragma unroll
+          for (int rs = 0; rs < 2; ++rs) {
+            split2(v[hf][rs][m].x, v[hf][rs][m].y, hi[4 * m + 2 * rs], lo[4 * m + 2 * rs]);
+            split2(v[hf][rs][m].z, v[hf][rs][m].w, hi[4 * m + 2 * rs + 1], lo[4 * m + 2 * rs + 1]);
+          }
+        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q + 16 * hf) << 16) + (uint32_t)(C::kAccCols + 64 * s);
+        tmem_st_16x256b_x4(taddr, hi);
+        tmem_st_16x256b_x4(taddr + 32, lo);
+      }
+      tmem_st_wait();                   // this thread's tensor-memory stores have completed ...
+      tc_fence_before();                // ... and are ordered before the arrive the MMA warp synchronises on
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[s]);
+    }
+    // ===================== epilogue: TMEM -> scale/shift/relu -> global =====================
+    constexpr int CPW = COUT / NG;                                           // accumulator columns per warp (>= 16)
+    static_assert(CPW >= 16 && CPW % 16 == 0, "tcgen05.ld granularity: 16 columns");
+    if (nlist > 0) {
+      mbar_wait(accum, 0u, a.hint_producer);
+      tc_fence_after();
+    }
+    const int row = row0 + q * 32 + lane;
+    float *obase = a.out + (size_t)blockIdx.z * a.n_out * a.cout_total;
+#pragma unroll
+    for (int cc = 0; cc < CPW; cc += 16) {
+      const int c0 = g * CPW + cc;
+      uint32_t r[16];
+      if (nlist > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      else {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) r[e] = 0u;             // no chunk of this split touches the tile: partial = 0
+      }
+      if (row < a.n_out) {
+        float *o = obase + (size_t)row * a.cout_total + col0 + c0;
+#pragma unroll
+        for (int gg = 0; gg < 4; ++gg) {
+          float4 y;
+          float *yy = (float *)&y;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int c = c0 + gg * 4 + e;
+            float val = fmaf(__uint_as_float(r[gg * 4 + e]), s_scale[c], s_shift[c]);
+            if (a.relu) val = fmaxf(val, 0.f);
+            yy[e] = val;
+          }
+          if (a.accumulate) {
+            const float4 prev = *(const float4 *)(o + gg * 4);
+            y.x += prev.x; y.y += prev.y; y.z += prev.z; y.w += prev.w;
+          }
+          *(float4 *)(o + gg * 4) = y;
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp == NPW) {
+    // ===================== B loader =====================
+    if (lane == 0) {
+      for (int i = 0; i < nlist; ++i) {
+        const int j = s_list[i];
+        const int sb = i % kStages;
+        const uint32_t ph = (uint32_t)(i / kStages) & 1u;
+        mbar_wait(&empty[sb], ph ^ 1u, a.hint_single);
+        mbar_arrive_expect_tx(&full[sb], (uint32_t)C::kBBytes);
+        const uint8_t *src = a.wpack + (size_t)j * 2 * a.cout_total * 128 + (size_t)col0 * 128;
+        uint8_t *dst = btiles + sb * C::kBBytes;
+        bulk_g2s(dst, src, (uint32_t)(COUT * 128), &full[sb]);
+        bulk_g2s(dst + COUT * 128, src + (size_t)a.cout_total * 128, (uint32_t)(COUT * 128), &full[sb]);
+      }
+    }
+  } else {
+    // ===================== MMA issuer (whole warp converged, tcgen05 instructions by one elected lane) =====================
+    constexpr uint32_t idesc = umma_idesc(COUT);
+    for (int i = 0; i < nlist; ++i) {
+      const int s = i % kStages;
+      mbar_wait(&full[s], (uint32_t)(i / kStages) & 1u, a.hint_single);   // A stage in tensor memory AND the weight chunk have landed
+      tc_fence_after();
+      const uint32_t ta = tmem_base + (uint32_t)(C::kAccCols + 64 * s);
+      const uint32_t sbm = smem_u32(btiles + s * C::kBBytes);
+      const uint32_t first = i == 0 ? 0u : 1u;
+      if (elect_one_sync()) {
+#pragma unroll
+        for (int ks = 0; ks < kChunk / 16; ++ks) {
+          const uint64_t bhi = umma_desc(sbm + ks * 32), blo = umma_desc(sbm + COUT * 128 + ks * 32);
+          umma_f16_ts(tmem_base, ta + 8 * ks, bhi, idesc, ks == 0 ? first : 1u);
+          umma_f16_ts(tmem_base, ta + 32 + 8 * ks, bhi, idesc, 1u);
+          umma_f16_ts(tmem_base, ta + 8 * ks, blo, idesc, 1u);
+        }
+        umma_commit(&empty[s]);          // TMEM stage and weight slot reusable once these MMAs have read them
+      }
+      __syncwarp();
+    }
+    if (nlist > 0 && elect_one_sync()) umma_commit(accum);   // accumulator complete
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == NPW + 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols));
+  }
+}
+
+template <int CIN, int COUT, int KOFF>
+static int launch(egn_ctx *ctx, const Args &a, const char *name, double bytes, double flops, cudaStream_t s) {
+  using C = Cfg<CIN, COUT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    EGN_CUDA(cudaFuncSetAttribute(k_sconv_ts<CIN, COUT, KOFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_done = true;
+  }
+  const dim3 grid((unsigned)div_up(a.n_out, kRows), (unsigned)(a.cout_total / COUT), (unsigned)a.ksplit);
+  EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv_ts<CIN, COUT, KOFF><<<grid, C::kThreads, C::kSmemBytes, s>>>(a));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+
+}  // namespace ts
+
+// dispatch of one (CIN, COUT-per-CTA, KOFF) instance; returns EGN_ERR_INVALID when there is no such instance
+int launch_conv_ts(egn_ctx *ctx, int koff, int cin, int cout_cta, const tcx::Args &a, const char *name, double bytes, double flops,
+                   cudaStream_t s) {
+#define EGN_TS_CASE(KO, CI, CO) \
+  if (koff == KO && cin == CI && cout_cta == CO) return ts::launch<CI, CO, KO>(ctx, a, name, bytes, flops, s);
+  EGN_TS_CASE(27, 32, 32)
+  EGN_TS_CASE(27, 32, 64)
+  EGN_TS_CASE(27, 64, 64)
+  EGN_TS_CASE(27, 64, 128)
+  EGN_TS_CASE(27, 128, 128)
+  EGN_TS_CASE(27, 128, 64)
+  EGN_TS_CASE(27, 128, 32)
+  EGN_TS_CASE(8, 32, 32)
+  EGN_TS_CASE(8, 64, 64)
+  EGN_TS_CASE(8, 128, 128)
+  EGN_TS_CASE(8, 128, 64)
+  EGN_TS_CASE(8, 128, 32)
+  EGN_TS_CASE(1, 32, 64)
+  EGN_TS_CASE(1, 64, 64)
+  EGN_TS_CASE(1, 64, 128)
+  EGN_TS_CASE(1, 128, 64)
+  EGN_TS_CASE(1, 128, 128)
+#undef EGN_TS_CASE
+  EGN_CHECK(false, EGN_ERR_INVALID, "tensor-core conv (TMEM-A): no kernel instance k=%d %d->%d", koff, cin, cout_cta);
+}
+
+}  // namespace egn
