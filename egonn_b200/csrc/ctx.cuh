@@ -55,6 +55,7 @@ struct Taps {  // device pointers of the last forward's feature maps (feature ar
   float *block[EGN_MAX_LEVELS] = {nullptr};
   int c_down[EGN_MAX_LEVELS] = {0}, c_block[EGN_MAX_LEVELS] = {0};
   int c0 = 0;
+  bool conv0_split = false, down_split[EGN_MAX_LEVELS] = {false}, block_split[EGN_MAX_LEVELS] = {false};   // pre-split maps (tc_ptx.cuh)
   float *gmap = nullptr, *lmap = nullptr;
   int c_g = 0, c_l = 0, lvl_g = 0, lvl_l = 0;
 };
@@ -113,7 +114,8 @@ int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, in
 // sconv_tc.cu
 bool sconv_tc_supported(int ksize, int transposed, int cin, int cout);
 int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const void *wpack,
-                const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s);
+                const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s, int in_split = 0,
+                int out_split = 0);
 // forward.cu
 int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float *features, float *global_out,
             float *desc_out, float *kp_out, float *sigma_out, cudaStream_t s);

@@ -7,7 +7,8 @@ namespace egn {
 
 // ops.cu
 int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const float *scale, const float *shift, int cout,
-              int relu, const int *not_ones, float *out, cudaStream_t s);
+              int relu, const int *not_ones, int out_split, float *out, cudaStream_t s);
+int run_presplit_to_f32(egn_ctx *ctx, const float *in, int64_t floats, float *out, cudaStream_t s);
 int run_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const float *w,
              const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s);
 int run_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, float p, float eps, float *part, int slices,
@@ -15,14 +16,21 @@ int run_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, float p,
 int run_gather_rows1(egn_ctx *ctx, const float *in, const int *perm, int n, float *out, int *not_ones, cudaStream_t s);
 int run_eca_gate(egn_ctx *ctx, int level, int c, const float *t, const float *wk, int k, float *part, int slices, float *gate,
                  cudaStream_t s);
-int run_eca_apply(egn_ctx *ctx, int level, int c, const float *t, const float *res, const float *gate, int relu, float *out,
-                  cudaStream_t s);
+int run_eca_apply(egn_ctx *ctx, int level, int c, const float *t, const float *res, const float *gate, int relu, int res_split,
+                  int out_split, float *out, cudaStream_t s);
 int run_l2norm(egn_ctx *ctx, const float *x, int n, int c, float *out, cudaStream_t s);
 int run_kp_sigma(egn_ctx *ctx, int level, const float *kp_raw, const float *sg_raw, int polar, const float q[3], int ignore_offset,
                  float *kp_out, float *sg_out, cudaStream_t s);
 int pool_slices_for(egn_ctx *ctx, int level);
 
 namespace {
+
+// A feature map of the running forward.  split: stored in the pre-split format of tc_ptx.cuh (bf16 hi/lo pairs + a zero
+// row at index n) because its main consumer is a tensor-core convolution that gathers from it.
+struct Map {
+  float *p = nullptr;
+  bool split = false;
+};
 
 struct Fwd {
   egn_ctx *ctx;
@@ -31,12 +39,31 @@ struct Fwd {
   cudaStream_t s;
   const float *W(int64_t off) const { return off < 0 ? nullptr : wb + off; }
   float *alloc(size_t floats) { return (float *)ctx->feats.take(floats * 4); }
+  // (n rows + the zero row of a pre-split map) x c
+  float *alloc_map(size_t n, int c) { return alloc((n + 1) * (size_t)c); }
+
+  bool tc_ok(const egn_layer &l, int ksize, int transposed) const {
+    return ctx->use_tc && l.wtc >= 0 && sconv_tc_supported(ksize, transposed, l.cin, l.cout);
+  }
+  // may a map whose main consumer is layer l be stored pre-split?
+  bool want_split(const egn_layer &l, int ksize, int transposed) const { return ctx->tc_variant == 1 && tc_ok(l, ksize, transposed); }
 
   // conv described by an egn_layer on the pyramid
-  int layer(const egn_layer &l, int level_in, int ksize, int transposed, const float *in, int relu, int accumulate, float *out) {
-    if (ctx->use_tc && l.wtc >= 0 && sconv_tc_supported(ksize, transposed, l.cin, l.cout))
-      return run_conv_tc(ctx, level_in, ksize, transposed, l.cin, l.cout, in, wb + l.wtc, W(l.scale), W(l.shift), relu, accumulate, out, s);
-    return run_conv(ctx, level_in, ksize, transposed, l.cin, l.cout, in, W(l.w), W(l.scale), W(l.shift), relu, accumulate, out, s);
+  int layer(const egn_layer &l, int level_in, int ksize, int transposed, Map in, int relu, int accumulate, Map out) {
+    const Pyramid &py = ctx->pyr;
+    if (tc_ok(l, ksize, transposed))
+      return run_conv_tc(ctx, level_in, ksize, transposed, l.cin, l.cout, in.p, wb + l.wtc, W(l.scale), W(l.shift), relu, accumulate, out.p, s,
+                         in.split, out.split);
+    EGN_CHECK(!out.split, EGN_ERR_STATE, "FP32 convolution asked to write a pre-split map");
+    const float *src = in.p;
+    if (in.split) {                                           // the FP32 CUDA-core kernels read fp32 only
+      const size_t floats = (size_t)py.n[level_in] * l.cin;
+      float *tmp = alloc(floats);
+      EGN_CHECK(tmp != nullptr, EGN_ERR_STATE, "feature arena exhausted (format conversion)");
+      EGN_TRY(run_presplit_to_f32(ctx, in.p, (int64_t)floats, tmp, s));
+      src = tmp;
+    }
+    return run_conv(ctx, level_in, ksize, transposed, l.cin, l.cout, src, W(l.w), W(l.scale), W(l.shift), relu, accumulate, out.p, s);
   }
 };
 
@@ -48,10 +75,11 @@ size_t head_floats(const Pyramid &py, const egn_head &h) {
 }
 
 size_t plan_floats(const Pyramid &py, const egn_net &net) {
-  size_t f = (size_t)py.n[0] + (size_t)py.n[0] * net.conv0.cout + 256;
+  size_t f = (size_t)py.n[0] + (size_t)(py.n[0] + 1) * net.conv0.cout + 256;
   for (int L = 1; L <= net.n_levels; ++L) {
-    const size_t n = py.n[L];
-    f += n * net.down[L].cout + 3 * n * net.conv2[L].cout + (net.res[L].cin ? n * net.res[L].cout : 0) + 512;
+    const size_t n = py.n[L] + 1;                          // + the zero row of pre-split maps
+    f += n * net.down[L].cout + 3 * n * net.conv2[L].cout + (net.res[L].cin ? n * net.res[L].cout : 0) + 1024;
+    f += 2 * n * net.conv2[L].cout;                        // fp32 copies for consumers that cannot read a pre-split map (rare)
     f += (size_t)py.n_batches * (64 + 1) * net.conv2[L].cout + 128;
   }
   f += head_floats(py, net.global_head) + head_floats(py, net.local_head);
@@ -69,19 +97,19 @@ size_t plan_floats(const Pyramid &py, const egn_net &net) {
 }
 
 // MinkHead.forward (models/minkgl.py:46-60): y = conv1x1[hi](x[hi]); for level hi-1..lo: y = tconv[level+1](y) (+ conv1x1[level](x[level]))
-int run_head(Fwd &F, const egn_head &h, float *const x[], float **out_map) {
+int run_head(Fwd &F, const egn_head &h, const Map x[], float **out_map) {
   const Pyramid &py = F.ctx->pyr;
   const int lo = h.levels[0], hi = h.levels[h.n_levels - 1];
   float *y = F.alloc((size_t)py.n[hi] * h.out_channels);
   EGN_CHECK(y != nullptr, EGN_ERR_STATE, "feature arena exhausted (head)");
-  EGN_TRY(F.layer(h.conv1x1[hi], hi, 1, 0, x[hi], 0, 0, y));
+  EGN_TRY(F.layer(h.conv1x1[hi], hi, 1, 0, x[hi], 0, 0, Map{y, false}));
   for (int level = hi - 1; level >= lo; --level) {
     float *y2 = F.alloc((size_t)py.n[level] * h.out_channels);
     EGN_CHECK(y2 != nullptr, EGN_ERR_STATE, "feature arena exhausted (head)");
-    EGN_TRY(F.layer(h.tconv[level + 1], level + 1, 2, 1, y, 0, 0, y2));
+    EGN_TRY(F.layer(h.tconv[level + 1], level + 1, 2, 1, Map{y, false}, 0, 0, Map{y2, false}));
     bool lateral = false;
     for (int i = 0; i < h.n_levels; ++i) lateral |= (h.levels[i] == level);
-    if (lateral) EGN_TRY(F.layer(h.conv1x1[level], level, 1, 0, x[level], 0, 1, y2));
+    if (lateral) EGN_TRY(F.layer(h.conv1x1[level], level, 1, 0, x[level], 0, 1, Map{y2, false}));
     y = y2;
   }
   *out_map = y;
@@ -109,18 +137,21 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
 
   // ---- trunk (models/minkgl.py:136-153) ----
   float *f0 = F.alloc(py.n[0]);
-  float *x0 = F.alloc((size_t)py.n[0] * net->conv0.cout);
-  EGN_CHECK(f0 && x0, EGN_ERR_STATE, "feature arena exhausted (conv0)");
+  Map x0;
+  x0.p = F.alloc_map(py.n[0], net->conv0.cout);
+  x0.split = F.want_split(net->down[1], 2, 0);
+  EGN_CHECK(f0 && x0.p, EGN_ERR_STATE, "feature arena exhausted (conv0)");
   int *not_ones = ctx->dev_counts + P + 3;
   EGN_TRY(run_gather_rows1(ctx, features, py.perm0, py.n[0], f0, not_ones, s));
   EGN_TRY(run_conv0(ctx, net->conv0_ksize, f0, F.W(net->conv0.w), F.W(net->conv0.scale), F.W(net->conv0.shift),
-                    net->conv0.cout, 1, not_ones, x0, s));
-  tp.conv0 = x0;
+                    net->conv0.cout, 1, not_ones, x0.split, x0.p, s));
+  tp.conv0 = x0.p;
+  tp.conv0_split = x0.split;
   tp.c0 = net->conv0.cout;
 
-  float *x[EGN_MAX_LEVELS] = {nullptr};
+  Map x[EGN_MAX_LEVELS];
   x[0] = x0;
-  const float *cur = x0;
+  Map cur = x0;
   // ---- local head (models/minkgl.py:288-308): needs only trunk levels <= max(local levels), so it is enqueued on the
   //      context's second stream as soon as that level is done and overlaps the small upper trunk levels ----
   auto run_local = [&](cudaStream_t ls) -> int {
@@ -136,13 +167,13 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
     float *s1 = F.alloc(n * net->sigma_mlp[0].cout), *s2 = F.alloc(n * net->sigma_mlp[1].cout);
     EGN_CHECK(d1 && d2 && k1 && k2 && s1 && s2, EGN_ERR_STATE, "feature arena exhausted (local mlps)");
     EGN_CHECK(net->kp_mlp[1].cout == 3 && net->sigma_mlp[1].cout == 1, EGN_ERR_INVALID, "keypoint/sigma regressor shapes");
-    EGN_TRY(F.layer(net->desc_mlp[0], lvl, 1, 0, lm, 1, 0, d1));
-    EGN_TRY(F.layer(net->desc_mlp[1], lvl, 1, 0, d1, 0, 0, d2));
+    EGN_TRY(F.layer(net->desc_mlp[0], lvl, 1, 0, Map{lm, false}, 1, 0, Map{d1, false}));
+    EGN_TRY(F.layer(net->desc_mlp[1], lvl, 1, 0, Map{d1, false}, 0, 0, Map{d2, false}));
     EGN_TRY(run_l2norm(ctx, d2, (int)n, net->desc_mlp[1].cout, desc_out, ls));
-    EGN_TRY(F.layer(net->kp_mlp[0], lvl, 1, 0, lm, 1, 0, k1));
-    EGN_TRY(F.layer(net->kp_mlp[1], lvl, 1, 0, k1, 0, 0, k2));
-    EGN_TRY(F.layer(net->sigma_mlp[0], lvl, 1, 0, lm, 1, 0, s1));
-    EGN_TRY(F.layer(net->sigma_mlp[1], lvl, 1, 0, s1, 0, 0, s2));
+    EGN_TRY(F.layer(net->kp_mlp[0], lvl, 1, 0, Map{lm, false}, 1, 0, Map{k1, false}));
+    EGN_TRY(F.layer(net->kp_mlp[1], lvl, 1, 0, Map{k1, false}, 0, 0, Map{k2, false}));
+    EGN_TRY(F.layer(net->sigma_mlp[0], lvl, 1, 0, Map{lm, false}, 1, 0, Map{s1, false}));
+    EGN_TRY(F.layer(net->sigma_mlp[1], lvl, 1, 0, Map{s1, false}, 0, 0, Map{s2, false}));
     EGN_TRY(run_kp_sigma(ctx, lvl, k2, s2, net->polar, net->quant_step, net->ignore_keypoint_regressor, kp_out, sigma_out, ls));
     return EGN_OK;
   };
@@ -151,15 +182,21 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
   for (int L = 1; L <= net->n_levels; ++L) {
     const size_t n = py.n[L];
     const int c = net->conv2[L].cout;
-    float *d = F.alloc(n * net->down[L].cout), *t1 = F.alloc(n * c), *t2 = F.alloc(n * c), *xo = F.alloc(n * c);
-    EGN_CHECK(d && t1 && t2 && xo, EGN_ERR_STATE, "feature arena exhausted (level %d)", L);
+    Map d, t1, t2, xo;
+    d.p = F.alloc_map(n, net->down[L].cout); t1.p = F.alloc_map(n, c); t2.p = F.alloc_map(n, c); xo.p = F.alloc_map(n, c);
+    EGN_CHECK(d.p && t1.p && t2.p && xo.p, EGN_ERR_STATE, "feature arena exhausted (level %d)", L);
+    // pre-split where the producer can write it (a tensor-core convolution / the fused residual pass) and the main consumer gathers it
+    d.split = F.tc_ok(net->down[L], 2, 0) && F.want_split(net->conv1[L], 3, 0);
+    t1.split = F.tc_ok(net->conv1[L], 3, 0) && F.want_split(net->conv2[L], 3, 0);
+    xo.split = L < net->n_levels && F.want_split(net->down[L + 1], 2, 0);
     EGN_TRY(F.layer(net->down[L], L - 1, 2, 0, cur, 1, 0, d));              // convs[L] + bn[L] + relu
     EGN_TRY(F.layer(net->conv1[L], L, 3, 0, d, 1, 0, t1));                  // conv1 + norm1 + relu
     EGN_TRY(F.layer(net->conv2[L], L, 3, 0, t1, 0, 0, t2));                 // conv2 + norm2
-    const float *res = d;
+    Map res = d;
     if (net->res[L].cin) {                                                  // downsample: 1x1 + bn
-      float *r = F.alloc(n * c);
-      EGN_CHECK(r != nullptr, EGN_ERR_STATE, "feature arena exhausted (residual)");
+      Map r;
+      r.p = F.alloc_map(n, c);
+      EGN_CHECK(r.p != nullptr, EGN_ERR_STATE, "feature arena exhausted (residual)");
       EGN_TRY(F.layer(net->res[L], L, 1, 0, d, 0, 0, r));
       res = r;
     } else {
@@ -170,14 +207,14 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
       const int slices = pool_slices_for(ctx, L);
       float *part = F.alloc((size_t)py.n_batches * slices * c), *g = F.alloc((size_t)py.n_batches * c);
       EGN_CHECK(part && g, EGN_ERR_STATE, "feature arena exhausted (eca)");
-      EGN_TRY(run_eca_gate(ctx, L, c, t2, F.W(net->eca_w[L]), net->eca_k[L], part, slices, g, s));
+      EGN_TRY(run_eca_gate(ctx, L, c, t2.p, F.W(net->eca_w[L]), net->eca_k[L], part, slices, g, s));
       gate = g;
     }
-    EGN_TRY(run_eca_apply(ctx, L, c, t2, res, gate, 1, xo, s));             // out = relu(eca(out) + residual)
+    EGN_TRY(run_eca_apply(ctx, L, c, t2.p, res.p, gate, 1, res.split, xo.split, xo.p, s));   // out = relu(eca(out) + residual)
     x[L] = xo;
     cur = xo;
-    tp.down[L] = d; tp.c_down[L] = net->down[L].cout;
-    tp.block[L] = xo; tp.c_block[L] = c;
+    tp.down[L] = d.p; tp.c_down[L] = net->down[L].cout; tp.down_split[L] = d.split;
+    tp.block[L] = xo.p; tp.c_block[L] = c; tp.block_split[L] = xo.split;
     if (L == local_top) {
       if (L < net->n_levels && ctx->aux && !ctx->prof.on) {               // fork: local head || levels L+1..n + global head
         EGN_CUDA(cudaEventRecord(ctx->ev_fork, s));
@@ -203,8 +240,8 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
     if (net->global_mlp[0].cin) {
       float *m1 = F.alloc((size_t)py.n[lvl] * net->global_mlp[0].cout), *m2 = F.alloc((size_t)py.n[lvl] * net->global_mlp[1].cout);
       EGN_CHECK(m1 && m2, EGN_ERR_STATE, "feature arena exhausted (global mlp)");
-      EGN_TRY(F.layer(net->global_mlp[0], lvl, 1, 0, gm, 1, 0, m1));
-      EGN_TRY(F.layer(net->global_mlp[1], lvl, 1, 0, m1, 0, 0, m2));
+      EGN_TRY(F.layer(net->global_mlp[0], lvl, 1, 0, Map{gm, false}, 1, 0, Map{m1, false}));
+      EGN_TRY(F.layer(net->global_mlp[1], lvl, 1, 0, Map{m1, false}, 0, 0, Map{m2, false}));
       pin = m2;
       c = net->global_mlp[1].cout;
     }
@@ -225,12 +262,14 @@ int forward_tap(egn_ctx *ctx, int which, int level, float *out, cudaStream_t s) 
   const Taps &tp = ctx->taps;
   const float *src = nullptr;
   size_t floats = 0;
-  if (which == 0) { src = tp.conv0; floats = (size_t)py.n[0] * tp.c0; }
-  else if (which == 1 && level >= 1 && level < EGN_MAX_LEVELS) { src = tp.down[level]; floats = (size_t)py.n[level] * tp.c_down[level]; }
-  else if (which == 2 && level >= 1 && level < EGN_MAX_LEVELS) { src = tp.block[level]; floats = (size_t)py.n[level] * tp.c_block[level]; }
+  bool split = false;
+  if (which == 0) { src = tp.conv0; floats = (size_t)py.n[0] * tp.c0; split = tp.conv0_split; }
+  else if (which == 1 && level >= 1 && level < EGN_MAX_LEVELS) { src = tp.down[level]; floats = (size_t)py.n[level] * tp.c_down[level]; split = tp.down_split[level]; }
+  else if (which == 2 && level >= 1 && level < EGN_MAX_LEVELS) { src = tp.block[level]; floats = (size_t)py.n[level] * tp.c_block[level]; split = tp.block_split[level]; }
   else if (which == 3) { src = tp.gmap; floats = (size_t)py.n[tp.lvl_g] * tp.c_g; }
   else if (which == 4) { src = tp.lmap; floats = (size_t)py.n[tp.lvl_l] * tp.c_l; }
   EGN_CHECK(src != nullptr, EGN_ERR_STATE, "forward_tap: tap %d/%d not available", which, level);
+  if (split) return run_presplit_to_f32(ctx, src, (int64_t)floats, out, s);    // taps are always fp32
   EGN_CUDA(cudaMemcpyAsync(out, src, floats * 4, cudaMemcpyDeviceToDevice, s));
   return EGN_OK;
 }

@@ -16,8 +16,12 @@
 #include <type_traits>
 
 #include "ctx.cuh"
+#include "tc_ptx.cuh"
 
 namespace egn {
+
+using tcx::presplit_pack;
+using tcx::presplit_unpack;
 
 // ------------------------------------------------------------------------------------------------------
 // generic gathered convolution
@@ -197,11 +201,12 @@ __global__ void __launch_bounds__(C0<ONES>::kWarps * 32, C0<ONES>::kCtas) k_conv
                                                             const uint64_t *__restrict__ mask64, const int *__restrict__ first0, int n0,
                                                             const float *__restrict__ w /* (KS^3,1,32) */, const float *__restrict__ scale,
                                                             const float *__restrict__ shift, int relu, const int *__restrict__ not_ones,
-                                                            float *__restrict__ out) {
+                                                            int out_split, float *__restrict__ out) {
   constexpr int KV = KS * KS * KS, R = KS / 2, COUT = 32, kC0Warps = C0<ONES>::kWarps;
   using entry_t = typename std::conditional<ONES, uint8_t, uint32_t>::type;
   const bool all_ones = not_ones != nullptr && *not_ones == 0;
   if (all_ones != ONES) return;
+  if (out_split && blockIdx.x == 0 && threadIdx.x < COUT) out[(size_t)n0 * COUT + threadIdx.x] = 0.f;   // the zero row of a pre-split map
   extern __shared__ __align__(16) uint8_t s_raw[];
   float *s_w = (float *)s_raw;                                           // [KV][36]
   unsigned long long *s_box = (unsigned long long *)(s_w + KV * kC0WStride + 4);   // [axis 3][l 4][delta 3]
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(C0<ONES>::kWarps * 32, C0<ONES>::kCtas) k_conv
           if (relu) v = fmaxf(v, 0.f);
           yy[e] = v;
         }
-        o[c4] = y;
+        if (out_split) ((uint4 *)o)[c4] = presplit_pack(y); else o[c4] = y;
       }
     }
     __syncwarp();
@@ -380,9 +385,11 @@ __global__ void k_eca_gate(const float *__restrict__ part, const int *__restrict
     gate[(size_t)b * c + ch] = 1.f / (1.f + expf(-y));
   }
 }
-// out = relu(t * gate[batch(row)] + res)   (layers/eca_block.py:36,70-71); gate == null -> plain BasicBlock
+// out = relu(t * gate[batch(row)] + res)   (layers/eca_block.py:36,70-71); gate == null -> plain BasicBlock.
+// res_split / out_split: the residual / the output is a pre-split map (tc_ptx.cuh); out_split also writes the zero row.
 __global__ void k_eca_apply(const float4 *__restrict__ t, const float4 *__restrict__ res, const float *__restrict__ gate,
-                            const uint64_t *__restrict__ keys, int batch_shift, int n, int c4, int relu, float4 *__restrict__ out) {
+                            const uint64_t *__restrict__ keys, int batch_shift, int n, int c4, int relu, int res_split, int out_split,
+                            float4 *__restrict__ out) {
   const int64_t total = (int64_t)n * c4;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / c4), q = (int)(i % c4);
@@ -392,10 +399,18 @@ __global__ void k_eca_apply(const float4 *__restrict__ t, const float4 *__restri
       const float4 g = *(const float4 *)(gate + ((size_t)b * c4 + q) * 4);
       v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
     }
-    if (res) { const float4 rr = res[i]; v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w; }
+    if (res) {
+      const float4 rr = res_split ? presplit_unpack(((const uint4 *)res)[i]) : res[i];
+      v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+    }
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    out[i] = v;
+    if (out_split) ((uint4 *)out)[i] = presplit_pack(v); else out[i] = v;
   }
+  if (out_split && blockIdx.x == 0 && (int)threadIdx.x < c4) out[total + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+// pre-split map -> fp32 (taps, and consumers that only read fp32)
+__global__ void k_presplit_to_f32(const uint4 *__restrict__ in, int64_t n4, float4 *__restrict__ out) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) out[i] = presplit_unpack(in[i]);
 }
 __global__ void k_bcast_mul(const float *__restrict__ x, const float *__restrict__ g, const uint64_t *__restrict__ keys,
                             int batch_shift, int n, int c, float *__restrict__ out) {
@@ -554,7 +569,7 @@ __global__ void __launch_bounds__(kTopkThreads) k_topk_smallest(const float *__r
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------
 int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const float *scale, const float *shift, int cout,
-              int relu, const int *not_ones, float *out, cudaStream_t s) {
+              int relu, const int *not_ones, int out_split, float *out, cudaStream_t s) {
   const Pyramid &py = ctx->pyr;
   EGN_CHECK(ksize == 5 || ksize == 3, EGN_ERR_INVALID, "conv0: kernel size %d not supported (3 or 5)", ksize);
   EGN_CHECK(cout == 32, EGN_ERR_INVALID, "conv0: %d output channels not supported (the egonn / MinkLoc3D stems use 32)", cout);
@@ -578,10 +593,10 @@ int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const fl
     if (not_ones)                                                                                                           \
       EGN_LAUNCH(ctx, NAME, bytes, flops, s,                                                                                \
                  k_conv0<KS, true><<<blocks1, C0<true>::kWarps * 32, smem1, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], \
-                                                                                 py.mask64, py.first0, n0, w, scale, shift, relu, not_ones, out)); \
+                                                                                 py.mask64, py.first0, n0, w, scale, shift, relu, not_ones, out_split, out)); \
     EGN_LAUNCH(ctx, not_ones ? NAME "(general variant)" : NAME, not_ones ? 0.0 : bytes, not_ones ? 0.0 : flops, s,          \
                k_conv0<KS, false><<<blocks0, C0<false>::kWarps * 32, smem0, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], \
-                                                                                py.mask64, py.first0, n0, w, scale, shift, relu, not_ones, out)); \
+                                                                                py.mask64, py.first0, n0, w, scale, shift, relu, not_ones, out_split, out)); \
   }
   if (ksize == 5) EGN_C0(5, "conv0_5x5x5") else EGN_C0(3, "conv0_3x3x3")
 #undef EGN_C0
@@ -619,7 +634,7 @@ int run_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int
     pairs = a.n_out;
   } else if (ksize == 5) {
     EGN_CHECK(level_in == 0 && cin == 1 && !accumulate, EGN_ERR_INVALID, "conv k=5 is supported at level 0 with cin=1 only");
-    return run_conv0(ctx, 5, in, w, scale, shift, cout, relu, nullptr, out, s);
+    return run_conv0(ctx, 5, in, w, scale, shift, cout, relu, nullptr, 0, out, s);
   } else {
     EGN_CHECK(false, EGN_ERR_INVALID, "conv: unsupported kernel size %d", ksize);
   }
@@ -746,15 +761,22 @@ int run_eca_gate(egn_ctx *ctx, int level, int c, const float *t, const float *wk
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
 }
-int run_eca_apply(egn_ctx *ctx, int level, int c, const float *t, const float *res, const float *gate, int relu, float *out,
-                  cudaStream_t s) {
+int run_presplit_to_f32(egn_ctx *ctx, const float *in, int64_t floats, float *out, cudaStream_t s) {
+  if (floats <= 0) return EGN_OK;
+  EGN_LAUNCH(ctx, "presplit_to_f32", (double)floats * 8, 0, s,
+             k_presplit_to_f32<<<grid_for(floats / 4, 256), 256, 0, s>>>((const uint4 *)in, floats / 4, (float4 *)out));
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+int run_eca_apply(egn_ctx *ctx, int level, int c, const float *t, const float *res, const float *gate, int relu, int res_split,
+                  int out_split, float *out, cudaStream_t s) {
   const Pyramid &py = ctx->pyr;
   const int n = py.n[level];
   EGN_CHECK((c & 3) == 0, EGN_ERR_INVALID, "block channels must be a multiple of 4");
   if (n == 0) return EGN_OK;
   EGN_LAUNCH(ctx, "eca_apply_residual_relu", (double)n * c * 12, 0, s,
              k_eca_apply<<<grid_for((int64_t)n * (c / 4), 256), 256, 0, s>>>((const float4 *)t, (const float4 *)res, gate, py.keys[level],
-                                                                               kMortonBits - 3 * level, n, c / 4, relu, (float4 *)out));
+                                                                               kMortonBits - 3 * level, n, c / 4, relu, res_split, out_split, (float4 *)out));
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
 }

@@ -363,34 +363,37 @@ int launch_conv_ts(egn_ctx *ctx, int koff, int cin, int cout_cta, const tcx::Arg
                    cudaStream_t s);
 
 int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const void *wpack,
-                const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s) {
+                const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s, int in_split,
+                int out_split) {
   const Pyramid &py = ctx->pyr;
+  EGN_CHECK((!in_split && !out_split) || ctx->tc_variant == 1, EGN_ERR_INVALID, "pre-split feature maps need the TMEM-A kernels");
+  EGN_CHECK(!(out_split && accumulate), EGN_ERR_INVALID, "accumulate into a pre-split map is not supported");
   EGN_CHECK(py.valid, EGN_ERR_STATE, "conv before coords_build");
   EGN_CHECK(sconv_tc_supported(ksize, transposed, cin, cout), EGN_ERR_INVALID, "tensor-core conv: unsupported shape k=%d %d->%d", ksize, cin, cout);
   EGN_CHECK(((uintptr_t)wpack & 15) == 0 && ((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 15) == 0, EGN_ERR_INVALID,
             "tensor-core conv: pointers must be 16-byte aligned");
   tc::Args a = {};
-  a.in = in; a.out = out; a.wpack = (const uint8_t *)wpack; a.scale = scale; a.shift = shift; a.relu = relu; a.accumulate = accumulate; a.cout_total = cout; a.ksplit = 1; a.hint_producer = ctx->hint_producer; a.hint_single = ctx->hint_single; a.trace = (long long *)ctx->trace;
+  a.in = in; a.out = out; a.wpack = (const uint8_t *)wpack; a.scale = scale; a.shift = shift; a.relu = relu; a.accumulate = accumulate; a.cout_total = cout; a.ksplit = 1; a.hint_producer = ctx->hint_producer; a.hint_single = ctx->hint_single; a.trace = (long long *)ctx->trace; a.in_split = in_split; a.out_split = out_split; a.out_zero_row = out_split;
   long long pairs;
   char name[48];
   if (ksize == 1) {
     EGN_CHECK(level_in >= 0 && level_in < P, EGN_ERR_INVALID, "conv k=1: bad level");
-    a.mode = 0; a.n_out = py.n[level_in];
+    a.mode = 0; a.n_out = py.n[level_in]; a.zero_row = py.n[level_in];
     pairs = a.n_out;
     snprintf(name, sizeof(name), "tc_rowmm_c%d_%d", cin, cout);
   } else if (ksize == 3) {
     EGN_CHECK(level_in >= 1 && level_in < P, EGN_ERR_INVALID, "conv k=3: bad level");
-    a.mode = 1; a.n_out = py.n[level_in]; a.nbr = py.nbr[level_in];
+    a.mode = 1; a.n_out = py.n[level_in]; a.nbr = py.nbr[level_in]; a.zero_row = py.n[level_in];
     pairs = py.pairs27[level_in];
     snprintf(name, sizeof(name), "tc_conv3x3x3_c%d_%d", cin, cout);
   } else if (transposed) {
     EGN_CHECK(level_in >= 1 && level_in < P, EGN_ERR_INVALID, "transposed conv: bad level");
-    a.mode = 3; a.n_out = py.n[level_in - 1]; a.up = py.up[level_in - 1]; a.keys = py.keys[level_in - 1];
+    a.mode = 3; a.n_out = py.n[level_in - 1]; a.up = py.up[level_in - 1]; a.keys = py.keys[level_in - 1]; a.zero_row = py.n[level_in];
     pairs = a.n_out;
     snprintf(name, sizeof(name), "tc_tconv2x2x2s2_c%d_%d", cin, cout);
   } else {
     EGN_CHECK(level_in >= 0 && level_in + 1 < P, EGN_ERR_INVALID, "conv k=2: bad level");
-    a.mode = 2; a.n_out = py.n[level_in + 1]; a.cstart = py.cstart[level_in + 1]; a.cmask = py.cmask[level_in + 1];
+    a.mode = 2; a.n_out = py.n[level_in + 1]; a.cstart = py.cstart[level_in + 1]; a.cmask = py.cmask[level_in + 1]; a.zero_row = py.n[level_in];
     pairs = py.n[level_in];
     snprintf(name, sizeof(name), "tc_conv2x2x2s2_c%d_%d", cin, cout);
   }
@@ -406,7 +409,7 @@ int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, 
   if (cin == 128 && cout == 128 && (ksize == 3 || ksize == 2) && !accumulate) {
     const int tiles = (int)div_up(a.n_out, tc::kRows);
     if (tiles <= 74) {        // N = 32 -> <= 148 CTAs for <= 37 tiles; N = 64 -> <= 148 CTAs for <= 74 tiles
-      const int splits = !ctx->ksplit ? 1 : (ksize == 3 ? (tiles <= 37 ? 3 : 1) : 1);
+      const int splits = (!ctx->ksplit || out_split) ? 1 : (ksize == 3 ? (tiles <= 37 ? 3 : 1) : 1);
       tc::Args b = a;
       float *part = nullptr;
       if (splits > 1) {

@@ -41,7 +41,11 @@ struct Cfg {
   static constexpr int kSmemBytes = kStages * kBBytes + kRows * 27 * 4 + 2 * COUT * 4 + 1024;
 };
 
-template <int CIN, int COUT, int KOFF>
+// SPLIT_IN: the input feature map is in the engine's pre-split format (common.cuh: every 4 channels = 16 bytes
+// [hi0 hi1 hi2 hi3 | lo0 lo1 lo2 lo3] bf16 - what the producing kernel's epilogue wrote) AND has an all-zero row at
+// index a.zero_row that absent neighbours point to: the gather is then 16-byte loads straight into the tcgen05.st
+// registers - no conversion, no predication.  Otherwise: fp32 rows, predicated loads, bf16 hi/lo split in registers.
+template <int CIN, int COUT, int KOFF, bool SPLIT_IN>
 __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCtasPerSm) k_sconv_ts(Args a) {
   using C = Cfg<CIN, COUT>;
   constexpr int kStages = C::kStages, NG = C::kGroups;
@@ -64,6 +68,9 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kRows;
   const int col0 = blockIdx.y * COUT;     // N-split: this CTA computes output channels [col0, col0 + COUT)
+  // debug timeline (EGN_TRACE=1, tools/trace_conv.py): clock64 stamps of one mid-grid CTA; a.trace is null in production
+  const bool trc = a.trace != nullptr && blockIdx.x == (gridDim.x >> 1) && blockIdx.y == 0 && blockIdx.z == 0;
+  if (trc && tid == 0) a.trace[60 * 8 + 0] = clock64();
 
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -108,7 +115,7 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     for (int it = 0; it < NBR_ITERS; ++it) {
       const int t = tid + it * NT;
       if (t < kRows * KOFF) {
-        s_nbr[t] = src[it];
+        s_nbr[t] = (SPLIT_IN && src[it] < 0) ? a.zero_row : src[it];
         if (src[it] >= 0) {
           const int k = t % KOFF;
           const int j = CIN == 128 ? 2 * k : (CIN == 64 ? k : (k >> 1));
@@ -137,6 +144,7 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   __syncthreads();
   const int nlist = *s_nlist;
   const uint32_t tmem_base = *s_tmem;
+  if (trc && tid == 0) { a.trace[60 * 8 + 1] = clock64(); a.trace[61 * 8 + 0] = nlist; }
 
   if (warp < NPW) {
     // ===================== A producers: gather -> bf16 hi/lo split -> tcgen05.st =====================
@@ -148,50 +156,97 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
       const int jc = s_list[i];
       const int s = i % kStages;
       const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-      float4 v[2][2][4];                                     // [half][row select][m]
+      const uint32_t tstage = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(C::kAccCols + 64 * s);
+      const bool tr = trc && q == 0 && lane == 0 && i < 60;
+      if (tr) a.trace[i * 8 + 3] = clock64();
+      if constexpr (SPLIT_IN) {
+        uint4 v[2][2][4];                                    // [half][row select][m]: (hi01, hi23, lo01, lo23) of 4 channels
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf)
-#pragma unroll
-        for (int rs = 0; rs < 2; ++rs) {
-          const int *nb = nb_base + (16 * hf + 8 * rs) * KOFF;
-          if (CIN == 32) {
-            const int k0 = 2 * jc, k1 = 2 * jc + 1;
-            const int s0 = nb[k0], s1 = k1 < KOFF ? nb[k1] : -1;
-            const float *p0 = a.in + (size_t)(s0 >= 0 ? s0 : 0) * CIN + 4 * j4;
-            const float *p1 = a.in + (size_t)(s1 >= 0 ? s1 : 0) * CIN + 4 * j4;
-            ldg4_pred(p0, s0 >= 0, v[hf][rs][0]);
-            ldg4_pred(p0 + 16, s0 >= 0, v[hf][rs][1]);
-            ldg4_pred(p1, s1 >= 0, v[hf][rs][2]);
-            ldg4_pred(p1 + 16, s1 >= 0, v[hf][rs][3]);
-          } else {
-            const int k = CIN == 64 ? jc : (jc >> 1);
-            const int s0 = nb[k];
-            const float *p0 = a.in + (size_t)(s0 >= 0 ? s0 : 0) * CIN + (CIN == 128 ? (jc & 1) * 64 : 0) + 4 * j4;
-#pragma unroll
-            for (int m = 0; m < 4; ++m) ldg4_pred(p0 + 16 * m, s0 >= 0, v[hf][rs][m]);
-          }
-        }
-      mbar_wait(&empty[s], ph ^ 1u, a.hint_producer);
-      tc_fence_after();
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int m = 0; m < 4; ++m)
+        for (int hf = 0; hf < 2; ++hf)
 #pragma unroll
           for (int rs = 0; rs < 2; ++rs) {
-            split2(v[hf][rs][m].x, v[hf][rs][m].y, hi[4 * m + 2 * rs], lo[4 * m + 2 * rs]);
-            split2(v[hf][rs][m].z, v[hf][rs][m].w, hi[4 * m + 2 * rs + 1], lo[4 * m + 2 * rs + 1]);
+            const int *nb = nb_base + (16 * hf + 8 * rs) * KOFF;
+            if (CIN == 32) {
+              const int k0 = 2 * jc, k1 = 2 * jc + 1;
+              const int s0 = nb[k0], s1 = k1 < KOFF ? nb[k1] : a.zero_row;
+              const uint4 *p0 = reinterpret_cast<const uint4 *>(a.in + (size_t)s0 * CIN) + j4;
+              const uint4 *p1 = reinterpret_cast<const uint4 *>(a.in + (size_t)s1 * CIN) + j4;
+              v[hf][rs][0] = __ldg(p0);
+              v[hf][rs][1] = __ldg(p0 + 4);
+              v[hf][rs][2] = __ldg(p1);
+              v[hf][rs][3] = __ldg(p1 + 4);
+            } else {
+              const int k = CIN == 64 ? jc : (jc >> 1);
+              const uint4 *p0 = reinterpret_cast<const uint4 *>(a.in + (size_t)nb[k] * CIN + (CIN == 128 ? (jc & 1) * 64 : 0)) + j4;
+#pragma unroll
+              for (int m = 0; m < 4; ++m) v[hf][rs][m] = __ldg(p0 + 4 * m);
+            }
           }
-        const uint32_t taddr = tmem_base + ((uint32_t)(32 * q + 16 * hf) << 16) + (uint32_t)(C::kAccCols + 64 * s);
-        tmem_st_16x256b_x4(taddr, hi);
-        tmem_st_16x256b_x4(taddr + 32, lo);
+        if (tr) a.trace[i * 8 + 4] = clock64();
+        mbar_wait(&empty[s], ph ^ 1u, a.hint_producer);
+        tc_fence_after();
+        if (tr) a.trace[i * 8 + 5] = clock64();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int rs = 0; rs < 2; ++rs) {
+              hi[4 * m + 2 * rs] = v[hf][rs][m].x; hi[4 * m + 2 * rs + 1] = v[hf][rs][m].y;
+              lo[4 * m + 2 * rs] = v[hf][rs][m].z; lo[4 * m + 2 * rs + 1] = v[hf][rs][m].w;
+            }
+          tmem_st_16x256b_x4(tstage + ((uint32_t)(16 * hf) << 16), hi);
+          tmem_st_16x256b_x4(tstage + ((uint32_t)(16 * hf) << 16) + 32, lo);
+        }
+      } else {
+        float4 v[2][2][4];                                   // [half][row select][m]
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf)
+#pragma unroll
+          for (int rs = 0; rs < 2; ++rs) {
+            const int *nb = nb_base + (16 * hf + 8 * rs) * KOFF;
+            if (CIN == 32) {
+              const int k0 = 2 * jc, k1 = 2 * jc + 1;
+              const int s0 = nb[k0], s1 = k1 < KOFF ? nb[k1] : -1;
+              const float *p0 = a.in + (size_t)(s0 >= 0 ? s0 : 0) * CIN + 4 * j4;
+              const float *p1 = a.in + (size_t)(s1 >= 0 ? s1 : 0) * CIN + 4 * j4;
+              ldg4_pred(p0, s0 >= 0, v[hf][rs][0]);
+              ldg4_pred(p0 + 16, s0 >= 0, v[hf][rs][1]);
+              ldg4_pred(p1, s1 >= 0, v[hf][rs][2]);
+              ldg4_pred(p1 + 16, s1 >= 0, v[hf][rs][3]);
+            } else {
+              const int k = CIN == 64 ? jc : (jc >> 1);
+              const int s0 = nb[k];
+              const float *p0 = a.in + (size_t)(s0 >= 0 ? s0 : 0) * CIN + (CIN == 128 ? (jc & 1) * 64 : 0) + 4 * j4;
+#pragma unroll
+              for (int m = 0; m < 4; ++m) ldg4_pred(p0 + 16 * m, s0 >= 0, v[hf][rs][m]);
+            }
+          }
+        mbar_wait(&empty[s], ph ^ 1u, a.hint_producer);
+        tc_fence_after();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int m = 0; m < 4; ++m)
+#pragma unroll
+            for (int rs = 0; rs < 2; ++rs) {
+              split2(v[hf][rs][m].x, v[hf][rs][m].y, hi[4 * m + 2 * rs], lo[4 * m + 2 * rs]);
+              split2(v[hf][rs][m].z, v[hf][rs][m].w, hi[4 * m + 2 * rs + 1], lo[4 * m + 2 * rs + 1]);
+            }
+          tmem_st_16x256b_x4(tstage + ((uint32_t)(16 * hf) << 16), hi);
+          tmem_st_16x256b_x4(tstage + ((uint32_t)(16 * hf) << 16) + 32, lo);
+        }
       }
+      if (tr) a.trace[i * 8 + 6] = clock64();
       tmem_st_wait();                   // this thread's tensor-memory stores have completed ...
       tc_fence_before();                // ... and are ordered before the arrive the MMA warp synchronises on
       __syncwarp();
       if (lane == 0) mbar_arrive(&full[s]);
+      if (tr) a.trace[i * 8 + 7] = clock64();
     }
+    if (trc && warp == 0 && lane == 0) a.trace[60 * 8 + 2] = clock64();
     // ===================== epilogue: TMEM -> scale/shift/relu -> global =====================
     constexpr int CPW = COUT / NG;                                           // accumulator columns per warp (>= 16)
     static_assert(CPW >= 16 && CPW % 16 == 0, "tcgen05.ld granularity: 16 columns");
@@ -199,6 +254,7 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
       mbar_wait(accum, 0u, a.hint_producer);
       tc_fence_after();
     }
+    if (trc && warp == 0 && lane == 0) a.trace[60 * 8 + 3] = clock64();
     const int row = row0 + q * 32 + lane;
     float *obase = a.out + (size_t)blockIdx.z * a.n_out * a.cout_total;
 #pragma unroll
@@ -227,10 +283,18 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
             const float4 prev = *(const float4 *)(o + gg * 4);
             y.x += prev.x; y.y += prev.y; y.z += prev.z; y.w += prev.w;
           }
-          *(float4 *)(o + gg * 4) = y;
+          if (a.out_split) {                               // pre-split output: [hi0..3 | lo0..3] bf16 in the same 16 bytes
+            *(uint4 *)(o + gg * 4) = presplit_pack(y);
+          } else {
+            *(float4 *)(o + gg * 4) = y;
+          }
         }
       }
     }
+    // the all-zero row behind the last output row (what absent neighbours of the NEXT convolution point to)
+    if (a.out_zero_row && blockIdx.x == 0 && blockIdx.z == 0 && warp == 0)
+      for (int c = lane; c < COUT; c += 32) a.out[(size_t)a.n_out * a.cout_total + col0 + c] = 0.f;
+    if (trc && warp == 0 && lane == 0) a.trace[60 * 8 + 4] = clock64();
     tc_fence_before();
   } else if (warp == NPW) {
     // ===================== B loader =====================
@@ -252,8 +316,11 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     constexpr uint32_t idesc = umma_idesc(COUT);
     for (int i = 0; i < nlist; ++i) {
       const int s = i % kStages;
+      const bool tr = trc && lane == 0 && i < 60;
+      if (tr) a.trace[i * 8 + 0] = clock64();
       mbar_wait(&full[s], (uint32_t)(i / kStages) & 1u, a.hint_single);   // A stage in tensor memory AND the weight chunk have landed
       tc_fence_after();
+      if (tr) a.trace[i * 8 + 1] = clock64();
       const uint32_t ta = tmem_base + (uint32_t)(C::kAccCols + 64 * s);
       const uint32_t sbm = smem_u32(btiles + s * C::kBBytes);
       const uint32_t first = i == 0 ? 0u : 1u;
@@ -268,29 +335,36 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
         umma_commit(&empty[s]);          // TMEM stage and weight slot reusable once these MMAs have read them
       }
       __syncwarp();
+      if (tr) a.trace[i * 8 + 2] = clock64();
     }
     if (nlist > 0 && elect_one_sync()) umma_commit(accum);   // accumulator complete
     __syncwarp();
   }
   __syncthreads();
+  if (trc && tid == 0) a.trace[60 * 8 + 5] = clock64();
   if (warp == NPW + 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::kTmemCols));
   }
 }
 
-template <int CIN, int COUT, int KOFF>
-static int launch(egn_ctx *ctx, const Args &a, const char *name, double bytes, double flops, cudaStream_t s) {
+template <int CIN, int COUT, int KOFF, bool SPLIT_IN>
+static int launch1(egn_ctx *ctx, const Args &a, const char *name, double bytes, double flops, cudaStream_t s) {
   using C = Cfg<CIN, COUT>;
   static bool attr_done = false;
   if (!attr_done) {
-    EGN_CUDA(cudaFuncSetAttribute(k_sconv_ts<CIN, COUT, KOFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    EGN_CUDA(cudaFuncSetAttribute(k_sconv_ts<CIN, COUT, KOFF, SPLIT_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     attr_done = true;
   }
   const dim3 grid((unsigned)div_up(a.n_out, kRows), (unsigned)(a.cout_total / COUT), (unsigned)a.ksplit);
-  EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv_ts<CIN, COUT, KOFF><<<grid, C::kThreads, C::kSmemBytes, s>>>(a));
+  EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv_ts<CIN, COUT, KOFF, SPLIT_IN><<<grid, C::kThreads, C::kSmemBytes, s>>>(a));
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
+}
+
+template <int CIN, int COUT, int KOFF>
+static int launch(egn_ctx *ctx, const Args &a, const char *name, double bytes, double flops, cudaStream_t s) {
+  return a.in_split ? launch1<CIN, COUT, KOFF, true>(ctx, a, name, bytes, flops, s) : launch1<CIN, COUT, KOFF, false>(ctx, a, name, bytes, flops, s);
 }
 
 }  // namespace ts

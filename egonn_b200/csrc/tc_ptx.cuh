@@ -181,6 +181,27 @@ __device__ __forceinline__ void ldg4_pred(const float *p, bool pred, float4 &a) 
       : "l"(p), "r"((uint32_t)pred));
 }
 
+// ---- pre-split feature maps ---------------------------------------------------------------------------------------------
+// A feature map that only tensor-core convolutions gather from is stored PRE-SPLIT: same (n, C) x 4-byte footprint as
+// fp32, but every group of 4 channels is the 16 bytes [hi0 hi1 hi2 hi3 | lo0 lo1 lo2 lo3] (bf16; x = hi + lo to 2^-17
+// relative - exactly the rounding the tensor-core path applies to its A operand anyway).  The producing kernel's
+// epilogue splits each value ONCE; the ~8.5 gathers per value of a 3x3x3 convolution then move bits only.  Such a map
+// also carries one all-zero row at index n, which absent neighbours point to (no predication in the gather).
+__device__ __forceinline__ uint4 presplit_pack(float4 y) {
+  uint4 u;
+  split2(y.x, y.y, u.x, u.z);
+  split2(y.z, y.w, u.y, u.w);
+  return u;
+}
+__device__ __forceinline__ float4 presplit_unpack(uint4 u) {
+  float4 y;
+  y.x = __uint_as_float(u.x << 16) + __uint_as_float(u.z << 16);
+  y.y = __uint_as_float(u.x & 0xffff0000u) + __uint_as_float(u.z & 0xffff0000u);
+  y.z = __uint_as_float(u.y << 16) + __uint_as_float(u.w << 16);
+  y.w = __uint_as_float(u.y & 0xffff0000u) + __uint_as_float(u.w & 0xffff0000u);
+  return y;
+}
+
 // launch arguments of the tensor-core convolution kernels (k_sconv_tc: A staged in shared memory, k_sconv_ts: A in tensor memory)
 struct Args {
   const float *in;
@@ -195,6 +216,11 @@ struct Args {
   const uint32_t *cmask;
   const int *up;           // mode 3: parent row of every output (fine) row
   const uint64_t *keys;    // mode 3: key of every output row (kernel slice = key & 7)
+  // k_sconv_ts only: pre-split feature maps (common.cuh, "pre-split format")
+  int in_split;            // input rows are pre-split AND row zero_row of the input is all zeros
+  int zero_row;
+  int out_split;           // write the output pre-split
+  int out_zero_row;        // also write an all-zero row at index n_out of the output
 };
 
 }  // namespace tcx
