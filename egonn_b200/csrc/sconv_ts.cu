@@ -30,6 +30,7 @@ using namespace tcx;
 template <int CIN, int COUT>
 struct Cfg {
   static constexpr bool kBig = COUT == 128;
+  static constexpr bool kFold = COUT == 32;                // 2-instruction form: D[:, 0:64] += Ahi*[Bhi;Blo]^T, D[:, 0:32] += Alo*Bhi^T
   static constexpr int kGroups = kBig ? 4 : 2;             // producer groups; one warp per TMEM lane quarter in each
   static constexpr int kProducerWarps = 4 * kGroups;
   static constexpr int kStages = kBig ? 6 : 3;
@@ -38,7 +39,7 @@ struct Cfg {
   static constexpr int kAccCols = kBig ? 128 : 64;         // A stages start here; accumulator = columns [0, COUT)
   static constexpr int kThreads = (kProducerWarps + 2) * 32;
   static constexpr int kBBytes = 2 * COUT * 128;           // hi + lo image of one weight chunk
-  static constexpr int kSmemBytes = kStages * kBBytes + kRows * 27 * 4 + 2 * COUT * 4 + 1024;
+  static constexpr int kSmemBytes = kStages * kBBytes + kRows * 27 * 4 + 1024;
 };
 
 // SPLIT_IN: the input feature map is in the engine's pre-split format (common.cuh: every 4 channels = 16 bytes
@@ -55,9 +56,7 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *btiles = smem;                                         // B ring: [kStages][hi | lo] (COUT*128 bytes each image)
   int *s_nbr = (int *)(btiles + kStages * C::kBBytes);            // [kRows][KOFF]
-  float *s_scale = (float *)(s_nbr + kRows * 27);                 // [COUT]
-  float *s_shift = s_scale + COUT;                                // [COUT]
-  uint64_t *full = (uint64_t *)(s_shift + COUT);                  // [kStages]  A stage stored + weight chunk landed
+  uint64_t *full = (uint64_t *)(s_nbr + kRows * 27);              // [kStages]  A stage stored + weight chunk landed
   uint64_t *empty = full + kStages;                               // [kStages]  stage consumed by the tensor core
   uint64_t *accum = empty + kStages;                              // [1]
   uint32_t *s_tmem = (uint32_t *)(accum + 1);
@@ -72,6 +71,24 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   const bool trc = a.trace != nullptr && blockIdx.x == (gridDim.x >> 1) && blockIdx.y == 0 && blockIdx.z == 0;
   if (trc && tid == 0) a.trace[60 * 8 + 0] = clock64();
 
+  // neighbour rows of the tile: the global loads go out FIRST, their latency overlaps barrier setup and TMEM allocation
+  int src[NBR_ITERS];
+#pragma unroll
+  for (int it = 0; it < NBR_ITERS; ++it) {
+    const int t = tid + it * NT;
+    const int r = t / KOFF, k = t - r * KOFF, row = row0 + r;
+    src[it] = -1;
+    if (t < kRows * KOFF && row < a.n_out) {
+      if (a.mode == 0) src[it] = row;
+      else if (a.mode == 1) src[it] = __ldg(a.nbr + (int64_t)row0 * 27 + t);
+      else if (a.mode == 2) {
+        const uint32_t m = __ldg(a.cmask + row);
+        if ((m >> k) & 1u) src[it] = __ldg(a.cstart + row) + __popc(m & ((1u << k) - 1u));
+      } else {
+        if ((int)(__ldg(a.keys + row) & 7ull) == k) src[it] = __ldg(a.up + row);
+      }
+    }
+  }
   if (tid == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     for (int s = 0; s < kStages; ++s) {
@@ -80,36 +97,14 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     }
     mbar_init(accum, 1);
     fence_barrier_init();
-    s_present[0] = 0u;
-    s_present[1] = 0u;
   }
   if (warp == NPW + 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)), "r"((uint32_t)C::kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  for (int c = tid; c < COUT; c += NT) {
-    s_scale[c] = a.scale ? a.scale[col0 + c] : 1.f;
-    s_shift[c] = a.shift ? a.shift[col0 + c] : 0.f;
-  }
+  if (tid < 2) s_present[tid] = 0u;
   __syncthreads();                    // s_present zeroed before the atomics below
   {
-    int src[NBR_ITERS];
-#pragma unroll
-    for (int it = 0; it < NBR_ITERS; ++it) {
-      const int t = tid + it * NT;
-      const int r = t / KOFF, k = t - r * KOFF, row = row0 + r;
-      src[it] = -1;
-      if (t < kRows * KOFF && row < a.n_out) {
-        if (a.mode == 0) src[it] = row;
-        else if (a.mode == 1) src[it] = __ldg(a.nbr + (int64_t)row0 * 27 + t);
-        else if (a.mode == 2) {
-          const uint32_t m = __ldg(a.cmask + row);
-          if ((m >> k) & 1u) src[it] = __ldg(a.cstart + row) + __popc(m & ((1u << k) - 1u));
-        } else {
-          if ((int)(__ldg(a.keys + row) & 7ull) == k) src[it] = __ldg(a.up + row);
-        }
-      }
-    }
     uint32_t m0 = 0u, m1 = 0u;
 #pragma unroll
     for (int it = 0; it < NBR_ITERS; ++it) {
@@ -134,12 +129,17 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (tid == 0) {
+  if (warp == 0) {
+    // compact the ids of the non-empty chunks inside this CTA's K-split range: lane handles chunks lane and lane + 32
     const int j_lo = (int)(((int64_t)NCH * blockIdx.z) / a.ksplit), j_hi = (int)(((int64_t)NCH * (blockIdx.z + 1)) / a.ksplit);
-    int n = 0;
-    for (int j = j_lo; j < j_hi; ++j)
-      if ((s_present[j >> 5] >> (j & 31)) & 1u) s_list[n++] = j;
-    *s_nlist = n;
+    const uint32_t pm0 = s_present[0], pm1 = s_present[1];
+    const bool p0 = lane >= j_lo && lane < j_hi && ((pm0 >> lane) & 1u);
+    const bool p1 = lane + 32 >= j_lo && lane + 32 < j_hi && ((pm1 >> lane) & 1u);
+    const uint32_t b0 = __ballot_sync(0xffffffffu, p0), b1 = __ballot_sync(0xffffffffu, p1);
+    const uint32_t below = (1u << lane) - 1u;
+    if (p0) s_list[__popc(b0 & below)] = lane;
+    if (p1) s_list[__popc(b0) + __popc(b1 & below)] = lane + 32;
+    if (lane == 0) *s_nlist = __popc(b0) + __popc(b1);
   }
   __syncthreads();
   const int nlist = *s_nlist;
@@ -261,8 +261,15 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     for (int cc = 0; cc < CPW; cc += 16) {
       const int c0 = g * CPW + cc;
       uint32_t r[16];
-      if (nlist > 0) tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      else {
+      if (nlist > 0) {
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        if constexpr (C::kFold) {                            // + the hi*lo half of the folded accumulator
+          uint32_t r2[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(COUT + c0), r2);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+        }
+      } else {
 #pragma unroll
         for (int e = 0; e < 16; ++e) r[e] = 0u;             // no chunk of this split touches the tile: partial = 0
       }
@@ -274,8 +281,10 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
           float *yy = (float *)&y;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int c = c0 + gg * 4 + e;
-            float val = fmaf(__uint_as_float(r[gg * 4 + e]), s_scale[c], s_shift[c]);
+            const int c = col0 + c0 + gg * 4 + e;
+            float val = __uint_as_float(r[gg * 4 + e]);
+            if (a.scale) val *= __ldg(a.scale + c);
+            if (a.shift) val += __ldg(a.shift + c);
             if (a.relu) val = fmaxf(val, 0.f);
             yy[e] = val;
           }
@@ -313,7 +322,10 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     }
   } else {
     // ===================== MMA issuer (whole warp converged, tcgen05 instructions by one elected lane) =====================
-    constexpr uint32_t idesc = umma_idesc(COUT);
+    // COUT == 32 folds hi*[Bhi;Blo] into ONE N=64 instruction (the two weight images are adjacent rows of the same
+    // shared-memory tile); the epilogue adds the two 32-column halves: 8 instead of 12 instructions per chunk where the
+    // issue rate (~30 cycles per tcgen05.mma), not the tensor pipe (16 cycles at N=32), is the limit.
+    constexpr uint32_t idesc = umma_idesc(COUT), idesc2 = umma_idesc(2 * COUT);
     for (int i = 0; i < nlist; ++i) {
       const int s = i % kStages;
       const bool tr = trc && lane == 0 && i < 60;
@@ -327,10 +339,16 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
       if (elect_one_sync()) {
 #pragma unroll
         for (int ks = 0; ks < kChunk / 16; ++ks) {
-          const uint64_t bhi = umma_desc(sbm + ks * 32), blo = umma_desc(sbm + COUT * 128 + ks * 32);
-          umma_f16_ts(tmem_base, ta + 8 * ks, bhi, idesc, ks == 0 ? first : 1u);
-          umma_f16_ts(tmem_base, ta + 32 + 8 * ks, bhi, idesc, 1u);
-          umma_f16_ts(tmem_base, ta + 8 * ks, blo, idesc, 1u);
+          const uint64_t bhi = umma_desc(sbm + ks * 32);
+          if constexpr (C::kFold) {
+            umma_f16_ts(tmem_base, ta + 8 * ks, bhi, idesc2, ks == 0 ? first : 1u);      // Ahi * [Bhi ; Blo]^T -> columns [0, 2 COUT)
+            umma_f16_ts(tmem_base, ta + 32 + 8 * ks, bhi, idesc, 1u);                    // Alo * Bhi^T         -> columns [0, COUT)
+          } else {
+            const uint64_t blo = umma_desc(sbm + COUT * 128 + ks * 32);
+            umma_f16_ts(tmem_base, ta + 8 * ks, bhi, idesc, ks == 0 ? first : 1u);
+            umma_f16_ts(tmem_base, ta + 32 + 8 * ks, bhi, idesc, 1u);
+            umma_f16_ts(tmem_base, ta + 8 * ks, blo, idesc, 1u);
+          }
         }
         umma_commit(&empty[s]);          // TMEM stage and weight slot reusable once these MMAs have read them
       }
