@@ -50,6 +50,18 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(kernel_key):
+    """DRAM bytes per launch (ncu dram__bytes_read.sum + dram__bytes_write.sum) of the roofline kernel, from the committed
+    capture profiles/r01_traffic.json (written by tools/ncu_summary.py traffic ... from one `ncu --set full` pass)."""
+    path = os.path.join(REPO, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        t = json.load(f)
+    e = t.get(kernel_key)
+    return (e["dram_bytes_per_launch"], e.get("source")) if e else (None, None)
+
+
 def load_weights():
     path = os.path.join(REPO, "tests", "golden", "egonn_weights.pth")
     return torch.load(path, map_location="cpu", weights_only=True), "reference checkpoint (tests/golden/egonn_weights.pth)"
@@ -126,10 +138,11 @@ def run_reference(args, rank, world):
 
     for _ in range(max(1, min(args.warmup, 1))):
         step()
-    steps = max(1, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
+    # bounded sample: at most --steps steps and at most ~120 s of host time (one step = one cloud, ~0.9 s on 16 cores)
+    steps, t0 = 0, time.perf_counter()
+    while steps < max(1, args.steps) and (steps == 0 or time.perf_counter() - t0 < 120.0):
         step()
+        steps += 1
     dt = (time.perf_counter() - t0) / steps
     value = 1.0 / dt
     sample = f"{steps} step(s) of 1 cloud of {args.config} (quantise + forward + top-{TOPK}), torch CPU {cores} threads"
@@ -147,8 +160,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--config", default="cfg2", choices=list(synth.CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="clouds per GPU per step (default: the config's batch)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -324,10 +337,10 @@ def main():
         peak, peak_src = load_peaks()
         total_ms = sum(e["ms"] for e in prof) or 1.0
         # roofline kernel = the dominant KERNEL by device time; all instances of one kernel template count together
-        # (k_sconv_tc<CIN,COUT,27> at the seven pyramid levels is one kernel at seven problem sizes)
+        # (k_sconv_ts<CIN,COUT,27> at the seven pyramid levels is one kernel at seven problem sizes)
         groups = {}
         for e in prof:
-            key = "k_sconv_tc[3x3x3, all channel widths]" if e["name"].startswith("tc_conv3x3x3") else e["name"]
+            key = "k_sconv_ts[3x3x3, all channel widths]" if e["name"].startswith("tc_conv3x3x3") else e["name"]
             g = groups.setdefault(key, {"name": key, "ms": 0.0, "alg_bytes": 0.0, "launches": 0, "flops": 0.0})
             for k in ("ms", "alg_bytes", "launches", "flops"):
                 g[k] += e[k]
@@ -338,8 +351,9 @@ def main():
                          "GFLOPs": (e["flops"] / 1e9) / (e["ms"] / 1e3) if e["ms"] > 0 else None} for e in prof),
                        key=lambda r: -r["ms_per_step"])
         achieved = (top["alg_bytes"] / 1e9) / (top["ms"] / 1e3)
+        traffic, traffic_src = load_traffic(top["name"])
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                     "share_of_step": top["ms"] / total_ms,
                     "alg_bytes_per_launch": top["alg_bytes"] / max(top["launches"], 1),
                     "avg_launch_ms": top["ms"] / max(top["launches"], 1)}
@@ -384,7 +398,7 @@ def cpu_baseline(args, sd):
         torch.topk(s, k=min(TOPK, s.shape[0]), largest=False)
 
     step()
-    n = 3
+    n = 12
     t0 = time.perf_counter()
     for _ in range(n):
         step()

@@ -19,8 +19,8 @@ int run_eca_gate(egn_ctx *ctx, int level, int c, const float *t, const float *wk
 int run_eca_apply(egn_ctx *ctx, int level, int c, const float *t, const float *res, const float *gate, int relu, int res_split,
                   int out_split, float *out, cudaStream_t s);
 int run_l2norm(egn_ctx *ctx, const float *x, int n, int c, float *out, cudaStream_t s);
-int run_kp_sigma(egn_ctx *ctx, int level, const float *kp_raw, const float *sg_raw, int polar, const float q[3], int ignore_offset,
-                 float *kp_out, float *sg_out, cudaStream_t s);
+int run_kp_sigma(egn_ctx *ctx, int level, const float *kp_raw, int kp_stride, const float *sg_raw, int sg_stride, int polar,
+                 const float q[3], int ignore_offset, float *kp_out, float *sg_out, cudaStream_t s);
 int pool_slices_for(egn_ctx *ctx, int level);
 
 namespace {
@@ -91,7 +91,7 @@ size_t plan_floats(const Pyramid &py, const egn_net &net) {
   if (net.local_head.n_levels) {
     const size_t n = py.n[net.local_head.levels[0]];
     f += n * (net.desc_mlp[0].cout + net.desc_mlp[1].cout + net.kp_mlp[0].cout + net.kp_mlp[1].cout + net.sigma_mlp[0].cout +
-              net.sigma_mlp[1].cout) + 1024;
+              net.sigma_mlp[1].cout + net.kpsig_mlp[0].cout + net.kpsig_mlp[1].cout) + 2048;
   }
   return f + 4096;
 }
@@ -163,18 +163,28 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
     const size_t n = py.n[lvl];
     tp.lmap = lm; tp.c_l = h.out_channels; tp.lvl_l = lvl;
     float *d1 = F.alloc(n * net->desc_mlp[0].cout), *d2 = F.alloc(n * net->desc_mlp[1].cout);
-    float *k1 = F.alloc(n * net->kp_mlp[0].cout), *k2 = F.alloc(n * net->kp_mlp[1].cout);
-    float *s1 = F.alloc(n * net->sigma_mlp[0].cout), *s2 = F.alloc(n * net->sigma_mlp[1].cout);
-    EGN_CHECK(d1 && d2 && k1 && k2 && s1 && s2, EGN_ERR_STATE, "feature arena exhausted (local mlps)");
-    EGN_CHECK(net->kp_mlp[1].cout == 3 && net->sigma_mlp[1].cout == 1, EGN_ERR_INVALID, "keypoint/sigma regressor shapes");
+    EGN_CHECK(d1 && d2, EGN_ERR_STATE, "feature arena exhausted (local mlps)");
     EGN_TRY(F.layer(net->desc_mlp[0], lvl, 1, 0, Map{lm, false}, 1, 0, Map{d1, false}));
     EGN_TRY(F.layer(net->desc_mlp[1], lvl, 1, 0, Map{d1, false}, 0, 0, Map{d2, false}));
     EGN_TRY(run_l2norm(ctx, d2, (int)n, net->desc_mlp[1].cout, desc_out, ls));
-    EGN_TRY(F.layer(net->kp_mlp[0], lvl, 1, 0, Map{lm, false}, 1, 0, Map{k1, false}));
-    EGN_TRY(F.layer(net->kp_mlp[1], lvl, 1, 0, Map{k1, false}, 0, 0, Map{k2, false}));
-    EGN_TRY(F.layer(net->sigma_mlp[0], lvl, 1, 0, Map{lm, false}, 1, 0, Map{s1, false}));
-    EGN_TRY(F.layer(net->sigma_mlp[1], lvl, 1, 0, Map{s1, false}, 0, 0, Map{s2, false}));
-    EGN_TRY(run_kp_sigma(ctx, lvl, k2, s2, net->polar, net->quant_step, net->ignore_keypoint_regressor, kp_out, sigma_out, ls));
+    if (net->kpsig_mlp[0].cin) {                            // fused regressors: one 64 -> 32+32 layer, one (32+32) -> 3+1 layer
+      EGN_CHECK(net->kpsig_mlp[1].cout == 4, EGN_ERR_INVALID, "fused keypoint/sigma regressor must end in 3+1 outputs");
+      float *h1 = F.alloc(n * net->kpsig_mlp[0].cout), *o4 = F.alloc(n * 4);
+      EGN_CHECK(h1 && o4, EGN_ERR_STATE, "feature arena exhausted (local mlps)");
+      EGN_TRY(F.layer(net->kpsig_mlp[0], lvl, 1, 0, Map{lm, false}, 1, 0, Map{h1, false}));
+      EGN_TRY(F.layer(net->kpsig_mlp[1], lvl, 1, 0, Map{h1, false}, 0, 0, Map{o4, false}));
+      EGN_TRY(run_kp_sigma(ctx, lvl, o4, 4, o4 + 3, 4, net->polar, net->quant_step, net->ignore_keypoint_regressor, kp_out, sigma_out, ls));
+    } else {
+      float *k1 = F.alloc(n * net->kp_mlp[0].cout), *k2 = F.alloc(n * net->kp_mlp[1].cout);
+      float *s1 = F.alloc(n * net->sigma_mlp[0].cout), *s2 = F.alloc(n * net->sigma_mlp[1].cout);
+      EGN_CHECK(k1 && k2 && s1 && s2, EGN_ERR_STATE, "feature arena exhausted (local mlps)");
+      EGN_CHECK(net->kp_mlp[1].cout == 3 && net->sigma_mlp[1].cout == 1, EGN_ERR_INVALID, "keypoint/sigma regressor shapes");
+      EGN_TRY(F.layer(net->kp_mlp[0], lvl, 1, 0, Map{lm, false}, 1, 0, Map{k1, false}));
+      EGN_TRY(F.layer(net->kp_mlp[1], lvl, 1, 0, Map{k1, false}, 0, 0, Map{k2, false}));
+      EGN_TRY(F.layer(net->sigma_mlp[0], lvl, 1, 0, Map{lm, false}, 1, 0, Map{s1, false}));
+      EGN_TRY(F.layer(net->sigma_mlp[1], lvl, 1, 0, Map{s1, false}, 0, 0, Map{s2, false}));
+      EGN_TRY(run_kp_sigma(ctx, lvl, k2, 3, s2, 1, net->polar, net->quant_step, net->ignore_keypoint_regressor, kp_out, sigma_out, ls));
+    }
     return EGN_OK;
   };
   bool local_forked = false;

@@ -328,21 +328,39 @@ __global__ void k_gather_rows1(const float *__restrict__ in, const int *__restri
 
 // per-cloud column reduction, deterministic two-stage: block (b, s) reduces slice s of cloud b's rows.
 // mode 0: sum x ; 1: sum clamp(x, eps)^p (GeM) ; 2: max x
-__global__ void k_pool_partial(const float *__restrict__ x, const int *__restrict__ boff, int c, int slices, int mode,
-                               float p, float eps, float *__restrict__ part /* (B, slices, c) */) {
+// CTA (b, s): 256 threads = (256 / c4) row lanes x c4 float4 column groups; every row lane walks its rows of the slice
+// with 16-byte loads, the row lanes are then added in fixed order through shared memory (deterministic).
+__global__ void __launch_bounds__(256) k_pool_partial(const float *__restrict__ x, const int *__restrict__ boff, int c, int slices, int mode,
+                                                      float p, float eps, float *__restrict__ part /* (B, slices, c) */) {
+  __shared__ float4 s_acc[256];
   const int b = blockIdx.x, s = blockIdx.y;
   const int r0 = boff[b], r1 = boff[b + 1];
   const int len = r1 - r0;
   const int a0 = r0 + (int)(((int64_t)len * s) / slices), a1 = r0 + (int)(((int64_t)len * (s + 1)) / slices);
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float acc = mode == 2 ? -INFINITY : 0.f;
-    for (int r = a0; r < a1; ++r) {
-      const float v = x[(size_t)r * c + ch];
-      if (mode == 0) acc += v;
-      else if (mode == 1) acc += powf(fmaxf(v, eps), p);
-      else acc = fmaxf(acc, v);
+  const int c4 = c >> 2;                                    // c is a multiple of 4, c4 <= 256 (checked by the launcher)
+  const int lanes = 256 / c4, q = threadIdx.x % c4, rl = threadIdx.x / c4;
+  const float init = mode == 2 ? -INFINITY : 0.f;
+  float4 acc = make_float4(init, init, init, init);
+  if (rl < lanes) {
+    for (int r = a0 + rl; r < a1; r += lanes) {
+      const float4 v = *(const float4 *)(x + (size_t)r * c + 4 * q);
+      if (mode == 0) { acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+      else if (mode == 1) {
+        acc.x += powf(fmaxf(v.x, eps), p); acc.y += powf(fmaxf(v.y, eps), p);
+        acc.z += powf(fmaxf(v.z, eps), p); acc.w += powf(fmaxf(v.w, eps), p);
+      } else { acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y); acc.z = fmaxf(acc.z, v.z); acc.w = fmaxf(acc.w, v.w); }
     }
-    part[((size_t)b * slices + s) * c + ch] = acc;
+  }
+  s_acc[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < c4) {
+    float4 t = s_acc[threadIdx.x];
+    for (int l = 1; l < lanes; ++l) {
+      const float4 v = s_acc[l * c4 + threadIdx.x];
+      if (mode == 2) { t.x = fmaxf(t.x, v.x); t.y = fmaxf(t.y, v.y); t.z = fmaxf(t.z, v.z); t.w = fmaxf(t.w, v.w); }
+      else { t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w; }
+    }
+    *(float4 *)(part + ((size_t)b * slices + s) * c + 4 * threadIdx.x) = t;
   }
 }
 __global__ void k_pool_final(const float *__restrict__ part, const int *__restrict__ boff, int c, int slices, int mode, float p,
@@ -434,7 +452,8 @@ __global__ void k_l2norm_rows(const float *__restrict__ x, int n, int c, float *
   }
 }
 // keypoint offset tanh + Quantizer.keypoint_position (datasets/quantization.py:60-72, 93-103); sigma softplus
-__global__ void k_kp_sigma(const float *__restrict__ kp_raw /* (n,3) */, const float *__restrict__ sg_raw /* (n,1) */,
+__global__ void k_kp_sigma(const float *__restrict__ kp_raw /* (n,>=3), row stride kp_stride */, int kp_stride,
+                           const float *__restrict__ sg_raw /* (n,>=1), row stride sg_stride */, int sg_stride,
                            const uint64_t *__restrict__ keys, int level, int n, int polar, float q0, float q1, float q2,
                            int ignore_offset, float *__restrict__ kp_out, float *__restrict__ sg_out) {
   for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
@@ -445,7 +464,10 @@ __global__ void k_kp_sigma(const float *__restrict__ kp_raw /* (n,3) */, const f
                   cz = (float)((int)(vz << level) - kAxisBias);
       const float st = (float)(1 << level);
       float ox = 0.f, oy = 0.f, oz = 0.f;
-      if (!ignore_offset) { ox = tanhf(kp_raw[3 * (size_t)r]); oy = tanhf(kp_raw[3 * (size_t)r + 1]); oz = tanhf(kp_raw[3 * (size_t)r + 2]); }
+      if (!ignore_offset) {
+        const float *kr = kp_raw + (size_t)r * kp_stride;
+        ox = tanhf(kr[0]); oy = tanhf(kr[1]); oz = tanhf(kr[2]);
+      }
       const float qy = polar ? q1 : q0, qz = polar ? q2 : q0;
       // (c + 0.5) * q + off * (stride * q) / 2
       const float kx = __fadd_rn(__fmul_rn(cx + 0.5f, q0), __fmul_rn(__fmul_rn(ox, __fmul_rn(st, q0)), 0.5f));
@@ -461,7 +483,7 @@ __global__ void k_kp_sigma(const float *__restrict__ kp_raw /* (n,3) */, const f
       }
     }
     if (sg_out) {
-      const float x = sg_raw[r];
+      const float x = sg_raw[(size_t)r * sg_stride];
       sg_out[r] = x > 20.f ? x : log1pf(expf(x));
     }
   }
@@ -658,8 +680,9 @@ int run_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, float p,
   const Pyramid &py = ctx->pyr;
   const int B = py.n_batches;
   const int threads = c >= 256 ? 256 : (c < 32 ? 32 : c);
+  EGN_CHECK((c & 3) == 0 && c <= 1024 && ((uintptr_t)in & 15) == 0, EGN_ERR_INVALID, "pooling: channels must be a multiple of 4 (<= 1024), 16-byte aligned rows");
   EGN_LAUNCH(ctx, "global_pool", (double)py.n[level] * c * 4, 0, s,
-             k_pool_partial<<<dim3(B, slices), threads, 0, s>>>(in, py.boff[level], c, slices, mode, p, eps, part));
+             k_pool_partial<<<dim3(B, slices), 256, 0, s>>>(in, py.boff[level], c, slices, mode, p, eps, part));
   EGN_LAUNCH(ctx, "global_pool", (double)B * (slices + 1) * c * 4, 0, s,
              k_pool_final<<<B, threads, 0, s>>>(part, py.boff[level], c, slices, mode, p, out));
   EGN_CUDA(cudaGetLastError());
@@ -754,8 +777,9 @@ int run_eca_gate(egn_ctx *ctx, int level, int c, const float *t, const float *wk
                  cudaStream_t s) {
   const Pyramid &py = ctx->pyr;
   const int threads = c >= 256 ? 256 : (c < 32 ? 32 : c);
+  EGN_CHECK((c & 3) == 0 && c <= 1024, EGN_ERR_INVALID, "eca: channels must be a multiple of 4 (<= 1024)");
   EGN_LAUNCH(ctx, "eca_pool", (double)py.n[level] * c * 4, 0, s,
-             k_pool_partial<<<dim3(py.n_batches, slices), threads, 0, s>>>(t, py.boff[level], c, slices, 0, 1.f, 0.f, part));
+             k_pool_partial<<<dim3(py.n_batches, slices), 256, 0, s>>>(t, py.boff[level], c, slices, 0, 1.f, 0.f, part));
   EGN_LAUNCH(ctx, "eca_gate", (double)py.n_batches * (slices + 1) * c * 4, 0, s,
              k_eca_gate<<<py.n_batches, threads, (size_t)c * 4, s>>>(part, py.boff[level], c, slices, wk, k, gate));
   EGN_CUDA(cudaGetLastError());
@@ -786,13 +810,13 @@ int run_l2norm(egn_ctx *ctx, const float *x, int n, int c, float *out, cudaStrea
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
 }
-int run_kp_sigma(egn_ctx *ctx, int level, const float *kp_raw, const float *sg_raw, int polar, const float q[3], int ignore_offset,
-                 float *kp_out, float *sg_out, cudaStream_t s) {
+int run_kp_sigma(egn_ctx *ctx, int level, const float *kp_raw, int kp_stride, const float *sg_raw, int sg_stride, int polar,
+                 const float q[3], int ignore_offset, float *kp_out, float *sg_out, cudaStream_t s) {
   const Pyramid &py = ctx->pyr;
   const int n = py.n[level];
   if (n == 0) return EGN_OK;
   EGN_LAUNCH(ctx, "keypoint_position_sigma", (double)n * 40, 0, s,
-             k_kp_sigma<<<grid_for(n, 128), 128, 0, s>>>(kp_raw, sg_raw, py.keys[level], level, n, polar, q[0], q[1], q[2], ignore_offset,
+             k_kp_sigma<<<grid_for(n, 128), 128, 0, s>>>(kp_raw, kp_stride, sg_raw, sg_stride, py.keys[level], level, n, polar, q[0], q[1], q[2], ignore_offset,
                                                          kp_out, sg_out));
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;

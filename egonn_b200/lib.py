@@ -39,7 +39,8 @@ class Net(C.Structure):
                 ("global_head", Head), ("local_head", Head), ("global_mlp", Layer * 2),
                 ("pool_method", C.c_int32), ("gem_p", C.c_float), ("gem_eps", C.c_float),
                 ("desc_mlp", Layer * 2), ("kp_mlp", Layer * 2), ("sigma_mlp", Layer * 2),
-                ("polar", C.c_int32), ("quant_step", C.c_float * 3), ("ignore_keypoint_regressor", C.c_int32)]
+                ("polar", C.c_int32), ("quant_step", C.c_float * 3), ("ignore_keypoint_regressor", C.c_int32),
+                ("kpsig_mlp", Layer * 2)]
 
 
 class ProfileEntry(C.Structure):

@@ -75,11 +75,31 @@ def _conv(blob, kernel, bn=None) -> L.Layer:
     return lay
 
 
-def _linear(blob, sd, prefix) -> L.Layer:
-    w = sd[prefix + ".linear.weight"]                     # (out, in)
+def _dense(blob, w_io: torch.Tensor, bias: Optional[torch.Tensor], pad_in: int = 0, pad_out: int = 0) -> L.Layer:
+    """(in, out) matrix [+ bias] -> row-wise layer, optionally zero-padded to (pad_in, pad_out) so that it has a
+    tensor-core instance (the padded hidden channels are exact zeros: relu(0 * x + 0) = 0 feeds zero weight rows)."""
+    cin, cout = w_io.shape
+    pi, po = max(pad_in, cin), max(pad_out, cout)
+    w = torch.zeros((pi, po), dtype=torch.float32)
+    w[:cin, :cout] = w_io
+    lay = L.Layer(cin=pi, cout=po, w=blob.add(w), scale=-1, shift=-1, wtc=-1)
+    if bias is not None:
+        b = torch.zeros(po, dtype=torch.float32)
+        b[:cout] = bias
+        lay.shift = blob.add(b)
+    if (pi, po) in TC_SHAPES.get(1, ()):
+        lay.wtc = blob.add(pack_tc(w.unsqueeze(0)).view(torch.float32))
+    return lay
+
+
+def _linear(blob, sd, prefix, pad_in: int = 0, pad_out: int = 0) -> L.Layer:
+    w = sd[prefix + ".linear.weight"].detach().to(torch.float32).cpu()     # (out, in)
+    bias = sd.get(prefix + ".linear.bias")
+    if pad_in or pad_out:
+        return _dense(blob, w.t(), None if bias is None else bias.detach().to(torch.float32).cpu(), pad_in, pad_out)
     lay = L.Layer(cin=w.shape[1], cout=w.shape[0], w=blob.add(w.t()), scale=-1, shift=-1, wtc=-1)
-    if prefix + ".linear.bias" in sd:
-        lay.shift = blob.add(sd[prefix + ".linear.bias"])
+    if bias is not None:
+        lay.shift = blob.add(bias)
     return lay
 
 
@@ -133,6 +153,25 @@ def pack_egonn(sd: Dict[str, torch.Tensor], quantizer_desc: dict, global_levels=
                           ("local_sigma_regressor", net.sigma_mlp)):
             dst[0] = _linear(blob, sd, name + ".net.0")
             dst[1] = _linear(blob, sd, name + ".net.2")
+        # tensor-core forms of the per-voxel MLPs (models/minkgl.py:175-225): hidden widths padded to a channel count with
+        # a tcgen05 instance (96 -> 128), and the two regressors that read the same map fused into one layer pair
+        hid = net.desc_mlp[0].cout
+        if (lc, 128) in TC_SHAPES[1] and hid <= 128 and net.desc_mlp[1].cout == 128:
+            net.desc_mlp[0] = _linear(blob, sd, "local_descriptor_decoder.net.0", pad_out=128)
+            net.desc_mlp[1] = _linear(blob, sd, "local_descriptor_decoder.net.2", pad_in=128)
+        kw0, sw0 = sd["local_keypoint_regressor.net.0.linear.weight"], sd["local_sigma_regressor.net.0.linear.weight"]
+        kw1, sw1 = sd["local_keypoint_regressor.net.2.linear.weight"], sd["local_sigma_regressor.net.2.linear.weight"]
+        hk, hs = kw0.shape[0], sw0.shape[0]
+        if kw1.shape[0] == 3 and sw1.shape[0] == 1 and (lc, hk + hs) in TC_SHAPES[1]:
+            f32 = lambda t: t.detach().to(torch.float32).cpu()
+            w0 = torch.cat([f32(kw0).t(), f32(sw0).t()], dim=1)                                    # (lc, hk + hs)
+            b0 = torch.cat([f32(sd["local_keypoint_regressor.net.0.linear.bias"]), f32(sd["local_sigma_regressor.net.0.linear.bias"])])
+            w1 = torch.zeros((hk + hs, 4))
+            w1[:hk, :3] = f32(kw1).t()
+            w1[hk:, 3:] = f32(sw1).t()
+            b1 = torch.cat([f32(sd["local_keypoint_regressor.net.2.linear.bias"]), f32(sd["local_sigma_regressor.net.2.linear.bias"])])
+            net.kpsig_mlp[0] = _dense(blob, w0, b0)
+            net.kpsig_mlp[1] = _dense(blob, w1, b1)
     net.polar = 1 if quantizer_desc["coordinates"] == "polar" else 0
     step = quantizer_desc["step"]
     step = list(step) if isinstance(step, (list, tuple)) else [step, step, step]

@@ -141,6 +141,10 @@ typedef struct {
   int32_t polar;                          /* keypoint_position: datasets/quantization.py:60-72 / :93-103 */
   float quant_step[3];
   int32_t ignore_keypoint_regressor;      /* models/minkgl.py:296-299 */
+  /* Optional fused form of kp_mlp + sigma_mlp (cin == 0: absent, the separate layers are used): both regressors read the same
+   * local map, so their first Linear layers run as ONE 64 -> 32+32 layer and their second layers as ONE block-diagonal
+   * (32+32) -> 3+1 layer; identical arithmetic per output (the extra weights are exact zeros).  models/minkgl.py:175-204 */
+  egn_layer kpsig_mlp[2];
 } egn_net;
 
 /* Keep the weight blob resident in L2 across forwards: reserves a persisting-L2 carve-out

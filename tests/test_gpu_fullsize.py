@@ -137,14 +137,15 @@ def test_forward_invariances_full_size(cfg, cuda, weights):
     centre = (full["local_coords"][:, 1:].float() + 0.5) * voxel
     assert ((full["keypoints"] - centre).abs() <= 4 * voxel * (1 + 1e-5) + 1e-4).all()
 
-    # (1) batch independence: cloud j alone == cloud j inside the batch
+    # (1) batch independence: cloud j alone == cloud j inside the batch (not bit-identical: the slice partition of the
+    #     per-cloud pooling sums, hence their fp32 summation order, depends on the batch composition -> 5e-5)
     for j in (0, FULL[cfg] - 1):
         cj = E.batched_coordinates([coords[j]])
         single = model.forward_packed({"coords": cj, "features": ones(cj.shape[0])})
         assert torch.equal(single["local_coords"][:, 1:], full["local_coords"][off[j]:off[j + 1], 1:])
-        assert_close_rel(single["global"][0], full["global"][j], 1e-5, f"global of cloud {j} alone")
+        assert_close_rel(single["global"][0], full["global"][j], 5e-5, f"global of cloud {j} alone")
         for k in ("descriptors", "keypoints", "sigma"):
-            assert_close_rel(single[k], full[k][off[j]:off[j + 1]], 1e-5, f"{k} of cloud {j} alone")
+            assert_close_rel(single[k], full[k][off[j]:off[j + 1]], 5e-5, f"{k} of cloud {j} alone")
 
     # (2) shuffled input rows + duplicated rows: canonical order makes the result identical
     g = torch.Generator(device="cpu").manual_seed(3)
@@ -161,9 +162,9 @@ def test_forward_invariances_full_size(cfg, cuda, weights):
     # (the canonical Morton row order changes under translation: compare keyed by coordinate)
     o1, o0 = torch.argsort(_lexkey(tr["local_coords"] - t)), torch.argsort(_lexkey(full["local_coords"]))
     assert torch.equal(tr["local_coords"][o1], full["local_coords"][o0] + t)
-    assert_close_rel(tr["global"], full["global"], 1e-5, "global under translation")
-    assert_close_rel(tr["descriptors"][o1], full["descriptors"][o0], 1e-5, "descriptors under translation")
-    assert_close_rel(tr["sigma"][o1], full["sigma"][o0], 1e-5, "sigma under translation")
+    assert_close_rel(tr["global"], full["global"], 5e-5, "global under translation")
+    assert_close_rel(tr["descriptors"][o1], full["descriptors"][o0], 5e-5, "descriptors under translation")
+    assert_close_rel(tr["sigma"][o1], full["sigma"][o0], 5e-5, "sigma under translation")
     assert_close_rel(tr["keypoints"][o1] - t[1:].float() * voxel, full["keypoints"][o0], 1e-4, "keypoints under translation")
 
     # (4) tensor-core (bf16x3 split) path == FP32 CUDA-core path

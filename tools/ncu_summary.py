@@ -9,7 +9,7 @@ import io
 import subprocess
 import sys
 
-KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+KEYS = ["gpu__time_duration.sum", "launch__grid_size_x", "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
         "launch__shared_mem_per_block_dynamic", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
@@ -42,9 +42,16 @@ def launches(path):
         print(f"{100 * t / total:6.1f}% {t:10.1f} {n:8d} {t / n:9.2f}  {name[:120]}")
 
 
-def full(path):
+def _raw_rows(path):
+    """rows of `ncu --page raw --csv`: from a .ncu-rep (converted here) or from a csv exported on the GPU box."""
+    if path.endswith(".csv"):
+        return list(csv.reader(open(path)))
     out = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True)
-    rows = list(csv.reader(io.StringIO(out)))
+    return list(csv.reader(io.StringIO(out)))
+
+
+def full(path):
+    rows = _raw_rows(path)
     hdr, units = rows[0], rows[1]
     for r in rows[2:]:
         print("== " + r[hdr.index("Kernel Name")][:140])
@@ -55,5 +62,30 @@ def full(path):
         print()
 
 
+def traffic(path):
+    """profiles/r01_traffic.json: per roofline kernel class, DRAM bytes per launch averaged over the captured launches."""
+    import json
+    rows = _raw_rows(path)
+    hdr, units = rows[0], rows[1]
+    i_name, i_r, i_w, i_t = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum"), hdr.index("gpu__time_duration.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    agg = {}
+    for r in rows[2:]:
+        name = r[i_name]
+        key = None
+        if "k_sconv_ts" in name and ", 27," in name.replace("(int)", ""):
+            key = "k_sconv_ts[3x3x3, all channel widths]"
+        if key is None:
+            continue
+        b = float(r[i_r].replace(",", "")) * scale[units[i_r]] + float(r[i_w].replace(",", "")) * scale[units[i_w]]
+        a = agg.setdefault(key, {"launches": 0, "dram_bytes": 0.0, "us": 0.0})
+        a["launches"] += 1
+        a["dram_bytes"] += b
+        a["us"] += float(r[i_t].replace(",", "")) / (1e3 if units[i_t] in ("ns", "nsecond") else 1.0)
+    res = {k: {"dram_bytes_per_launch": v["dram_bytes"] / v["launches"], "launches_captured": v["launches"],
+               "avg_us_under_ncu": v["us"] / v["launches"], "source": "ncu --set full, " + path.split("/")[-1]} for k, v in agg.items()}
+    print(json.dumps(res, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "full": full, "traffic": traffic}[sys.argv[1]](sys.argv[2])
