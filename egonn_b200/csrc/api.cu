@@ -285,6 +285,20 @@ int egn_knn_l2(egn_ctx *ctx, const float *query, const float *map, int n_query, 
   return op_knn_l2(ctx, query, map, n_query, n_map, dim, k, idx_out, dist_out, (cudaStream_t)stream);
 }
 
+int egn_match_mutual(egn_ctx *ctx, const float *desc_a, const float *desc_b, int n_a, int n_b, int dim, int mutual, int32_t *idx_out,
+                     float *dist_out, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return op_match_mutual(ctx, desc_a, desc_b, n_a, n_b, dim, mutual, idx_out, dist_out, (cudaStream_t)stream);
+}
+
+int egn_filter_points(egn_ctx *ctx, const float *records, int64_t n, int stride, int remove_zero, int remove_ground, float ground_level,
+                      float *points_out, int64_t *n_out, egn_stream_t stream) {
+  EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
+  DeviceGuard g(ctx->device);
+  return filter_points(ctx, records, n, stride, remove_zero, remove_ground, ground_level, points_out, n_out, (cudaStream_t)stream);
+}
+
 int egn_profile_enable(egn_ctx *ctx, int enable) {
   EGN_CHECK(ctx != nullptr, EGN_ERR_INVALID, "null ctx");
   ctx->prof.on = enable != 0;

@@ -675,4 +675,73 @@ int quantize(egn_ctx *ctx, const float *points, int64_t n64, const float step[3]
   return EGN_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// raw-scan ingest: PointCloudLoader.__call__ (misc/point_clouds.py:95-111) on the device - take the
+// xyz of every (x, y, z[, reflectance]) record, drop the all-zero points (np.isclose(pc, 0): |v| <= 1e-8) and the
+// points at or below the ground plane (z <= level), keep the input order.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_point_keep(const float *__restrict__ pts, int n, int stride, int remove_zero, int remove_ground, float ground,
+                             uint8_t *__restrict__ keep) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float x = pts[(size_t)i * stride], y = pts[(size_t)i * stride + 1], z = pts[(size_t)i * stride + 2];
+    bool k = true;
+    if (remove_zero && fabsf(x) <= 1e-8f && fabsf(y) <= 1e-8f && fabsf(z) <= 1e-8f) k = false;
+    if (remove_ground && !(z > ground)) k = false;
+    keep[i] = k ? 1 : 0;
+  }
+}
+__global__ void __launch_bounds__(kTileThreads) k_point_emit(const uint8_t *__restrict__ keep, const float *__restrict__ pts, int n, int stride,
+                                                             const int *__restrict__ base, float *__restrict__ out) {
+  __shared__ int s_wc[kWarpsPerTile];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int first = blockIdx.x * kTile + warp * (32 * kTileSteps);
+  int f[kTileSteps], cnt = 0;
+#pragma unroll
+  for (int s = 0; s < kTileSteps; ++s) {
+    const int i = first + s * 32 + lane;
+    f[s] = i < n ? keep[i] : 0;
+    cnt += __popc(__ballot_sync(0xffffffffu, f[s]));
+  }
+  if (lane == 0) s_wc[warp] = cnt;
+  __syncthreads();
+  int run = base[blockIdx.x];
+  for (int w = 0; w < warp; ++w) run += s_wc[w];
+#pragma unroll
+  for (int s = 0; s < kTileSteps; ++s) {
+    const int i = first + s * 32 + lane;
+    const uint32_t bal = __ballot_sync(0xffffffffu, f[s]);
+    if (f[s]) {
+      const int o = run + __popc(bal & ((1u << lane) - 1u));
+      out[3 * (size_t)o] = pts[(size_t)i * stride];
+      out[3 * (size_t)o + 1] = pts[(size_t)i * stride + 1];
+      out[3 * (size_t)o + 2] = pts[(size_t)i * stride + 2];
+    }
+    run += __popc(bal);
+  }
+}
+
+int filter_points(egn_ctx *ctx, const float *records, int64_t n64, int stride, int remove_zero, int remove_ground, float ground_level,
+                  float *points_out, int64_t *n_out, cudaStream_t s) {
+  EGN_CHECK(ctx && records && points_out && n_out, EGN_ERR_INVALID, "filter_points: null argument");
+  EGN_CHECK(n64 > 0 && n64 < (int64_t)1 << 28, EGN_ERR_INVALID, "filter_points: n out of range");
+  EGN_CHECK(stride >= 3, EGN_ERR_INVALID, "filter_points: a record has at least 3 floats (x, y, z)");
+  const int n = (int)n64;
+  const int nblocks = (int)div_up(n, kTile);
+  Arena &sc = ctx->scratch;
+  EGN_TRY(sc.reserve(pad256((size_t)n) + pad256((size_t)nblocks * 4) + 4096, s));
+  uint8_t *keep = (uint8_t *)sc.take((size_t)n);
+  int *counts = (int *)sc.take((size_t)nblocks * 4);
+  EGN_CHECK(keep && counts, EGN_ERR_STATE, "scratch arena exhausted");
+  EGN_CUDA(cudaMemsetAsync(ctx->dev_counts, 0, sizeof(HostCounts), s));
+  EGN_LAUNCH(ctx, "ingest_point_filter", (double)n * (stride * 4 + 1), 0, s,
+             k_point_keep<<<grid_for(n, 256), 256, 0, s>>>(records, n, stride, remove_zero, remove_ground, ground_level, keep));
+  EGN_LAUNCH(ctx, "ingest_compact", (double)n, 0, s, k_keep_count<<<nblocks, kTileThreads, 0, s>>>(keep, n, counts));
+  EGN_LAUNCH(ctx, "ingest_compact", 0, 0, s, k_scan1<<<1, 1024, 0, s>>>(counts, nblocks, ctx->dev_counts + P + 2));
+  EGN_LAUNCH(ctx, "ingest_compact", (double)n * 25, 0, s, k_point_emit<<<nblocks, kTileThreads, 0, s>>>(keep, records, n, stride, counts, points_out));
+  EGN_CUDA(cudaMemcpyAsync(ctx->host, ctx->dev_counts, sizeof(HostCounts), cudaMemcpyDeviceToHost, s));
+  EGN_CUDA(cudaStreamSynchronize(s));
+  *n_out = ctx->host->n_out;
+  return EGN_OK;
+}
+
 }  // namespace egn

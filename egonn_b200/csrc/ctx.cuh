@@ -102,6 +102,8 @@ int coords_build_points(egn_ctx *ctx, const float *points, int64_t n, const int3
 int coords_get(egn_ctx *ctx, int level, int32_t *out, cudaStream_t s);
 int quantize(egn_ctx *ctx, const float *points, int64_t n, const float step[3], int polar, int32_t *coords_out,
              int64_t *index_out, int64_t *n_out, cudaStream_t s);
+int filter_points(egn_ctx *ctx, const float *records, int64_t n, int stride, int remove_zero, int remove_ground, float ground_level,
+                  float *points_out, int64_t *n_out, cudaStream_t s);
 // ops.cu
 int op_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const float *w,
             const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s);
@@ -110,6 +112,8 @@ int op_global_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, fl
 int op_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const float *g, float *out, cudaStream_t s);
 int op_knn_l2(egn_ctx *ctx, const float *query, const float *map, int Q, int M, int D, int k, int32_t *idx_out, float *dist_out,
               cudaStream_t s);
+int op_match_mutual(egn_ctx *ctx, const float *a, const float *b, int na, int nb, int d, int mutual, int32_t *idx_out, float *dist_out,
+                    cudaStream_t s);
 int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out, cudaStream_t s);
 // sconv_tc.cu
 bool sconv_tc_supported(int ksize, int transposed, int cin, int cout);

@@ -757,6 +757,68 @@ int op_knn_l2(egn_ctx *ctx, const float *query, const float *map, int Q, int M, 
   return EGN_OK;
 }
 
+// ---- local-descriptor matching ------------------------------------------------------------------------------
+// The correspondence step of eval/evaluate.py:381-399 (Open3D registration_ransac_based_on_feature_matching with
+// mutual_filter=True): nearest neighbour in descriptor space from every row of A in B, kept when it is mutual.
+// One CTA per row of `a`: the row sits in shared memory, thread t scans rows t, t+256, .. of `b` (squared L2 on the
+// difference), then a fixed-order argmin (ties: lower row) - deterministic.
+__global__ void __launch_bounds__(256) k_nn_rows(const float *__restrict__ a, const float *__restrict__ b, int nb, int d,
+                                                 int *__restrict__ idx, float *__restrict__ dist) {
+  extern __shared__ float s_row[];
+  __shared__ float s_best[256];
+  __shared__ int s_arg[256];
+  const int r = blockIdx.x;
+  for (int i = threadIdx.x; i < d; i += 256) s_row[i] = a[(size_t)r * d + i];
+  __syncthreads();
+  float best = INFINITY;
+  int arg = -1;
+  for (int j = threadIdx.x; j < nb; j += 256) {
+    const float *q = b + (size_t)j * d;
+    float ss = 0.f;
+    for (int i = 0; i < d; ++i) { const float t = q[i] - s_row[i]; ss = fmaf(t, t, ss); }
+    if (ss < best) { best = ss; arg = j; }
+  }
+  s_best[threadIdx.x] = best;
+  s_arg[threadIdx.x] = arg;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float v = s_best[threadIdx.x + o];
+      const int g = s_arg[threadIdx.x + o];
+      if (g >= 0 && (v < s_best[threadIdx.x] || (v == s_best[threadIdx.x] && g < s_arg[threadIdx.x]) || s_arg[threadIdx.x] < 0)) {
+        s_best[threadIdx.x] = v;
+        s_arg[threadIdx.x] = g;
+      }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { idx[r] = s_arg[0]; if (dist) dist[r] = s_arg[0] >= 0 ? sqrtf(s_best[0]) : INFINITY; }
+}
+__global__ void k_mutual_filter(int *__restrict__ idx_ab, const int *__restrict__ idx_ba, int na) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < na; i += gridDim.x * blockDim.x) {
+    const int j = idx_ab[i];
+    if (j >= 0 && idx_ba[j] != i) idx_ab[i] = -1;
+  }
+}
+
+int op_match_mutual(egn_ctx *ctx, const float *a, const float *b, int na, int nb, int d, int mutual, int32_t *idx_out, float *dist_out,
+                    cudaStream_t s) {
+  EGN_CHECK(ctx && a && b && idx_out, EGN_ERR_INVALID, "match: null argument");
+  EGN_CHECK(na >= 1 && nb >= 1 && d >= 1 && d <= 4096, EGN_ERR_INVALID, "match: bad sizes (na=%d nb=%d dim=%d)", na, nb, d);
+  EGN_LAUNCH(ctx, "match_nearest", (double)na * nb * d * 4.0, 3.0 * na * nb * d, s,
+             k_nn_rows<<<na, 256, (size_t)d * 4, s>>>(a, b, nb, d, idx_out, dist_out));
+  if (mutual) {
+    EGN_TRY(ctx->scratch.reserve(pad256((size_t)nb * 4) + 4096, s));
+    int *back = (int *)ctx->scratch.take((size_t)nb * 4);
+    EGN_CHECK(back != nullptr, EGN_ERR_STATE, "scratch arena exhausted");
+    EGN_LAUNCH(ctx, "match_nearest", (double)na * nb * d * 4.0, 3.0 * na * nb * d, s,
+               k_nn_rows<<<nb, 256, (size_t)d * 4, s>>>(b, a, na, d, back, nullptr));
+    EGN_LAUNCH(ctx, "match_mutual_filter", (double)na * 12, 0, s, k_mutual_filter<<<grid_for(na, 256), 256, 0, s>>>(idx_out, back, na));
+  }
+  EGN_CUDA(cudaGetLastError());
+  return EGN_OK;
+}
+
 // exported to forward.cu
 __global__ void k_fill_ones(float *__restrict__ out, int n) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = 1.0f;

@@ -253,6 +253,49 @@ def knn_global(query: torch.Tensor, map_embeddings: torch.Tensor, k: int):
     return idx, torch.gather(dist, 1, idx.clamp_min(0))
 
 
+def _shared_engine(device) -> "Engine":
+    key = torch.device(device).index or 0
+    if key not in _retrieval_engines:
+        _retrieval_engines[key] = Engine(torch.device("cuda", key))
+    return _retrieval_engines[key]
+
+
+def match_descriptors(desc_a: torch.Tensor, desc_b: torch.Tensor, mutual: bool = True):
+    """Correspondences between the local descriptors of two clouds - the feature-matching step of
+    eval/evaluate.py:381-399 (Open3D ransac_based_on_feature_matching, mutual_filter=True).  Returns (idx (n_a,) int64 row of
+    ``desc_b`` per row of ``desc_a``, -1 where the nearest neighbour is not mutual; dist (n_a,) f32).  CUDA tensors only."""
+    _need_cuda(desc_a, "desc_a")
+    _need_cuda(desc_b, "desc_b")
+    a = desc_a.detach().to(torch.float32).contiguous()
+    b = desc_b.detach().to(torch.float32).contiguous()
+    assert a.dim() == 2 and b.dim() == 2 and a.shape[1] == b.shape[1]
+    eng = _shared_engine(a.device)
+    idx = torch.empty((a.shape[0],), dtype=torch.int32, device=a.device)
+    dist = torch.empty((a.shape[0],), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        L.check(eng.lib.egn_match_mutual(eng._ctx, _ptr(a), _ptr(b), a.shape[0], b.shape[0], a.shape[1], int(mutual), _ptr(idx), _ptr(dist),
+                                         _stream()))
+    return idx.long(), dist
+
+
+def filter_points(records: torch.Tensor, remove_zero_points: bool = True, remove_ground_plane: bool = True,
+                  ground_plane_level: float = -1.5) -> torch.Tensor:
+    """PointCloudLoader.__call__ (misc/point_clouds.py:95-111) on the device: (n, >=3) f32 records (x, y, z[, reflectance]) ->
+    (m, 3) points without the all-zero points and the points at or below the ground plane, input order kept."""
+    _need_cuda(records, "records")
+    r = records.detach().to(torch.float32).contiguous()
+    assert r.dim() == 2 and r.shape[1] >= 3
+    out = torch.empty((r.shape[0], 3), dtype=torch.float32, device=r.device)
+    if r.shape[0] == 0:
+        return out
+    eng = _shared_engine(r.device)
+    n_out = C.c_int64(0)
+    with torch.cuda.device(r.device):
+        L.check(eng.lib.egn_filter_points(eng._ctx, _ptr(r), r.shape[0], r.shape[1], int(remove_zero_points), int(remove_ground_plane),
+                                          C.c_float(ground_plane_level), _ptr(out), C.byref(n_out), _stream()))
+    return out[: n_out.value]
+
+
 def topk_smallest(sigma: torch.Tensor, offsets: torch.Tensor, k: int) -> torch.Tensor:
     """Per-cloud indices of the k smallest sigma, ascending (eval/evaluate.py:352-361); -1 padded."""
     _need_cuda(sigma, "sigma")

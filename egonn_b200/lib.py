@@ -70,6 +70,8 @@ _SIGNATURES = {
     "egn_global_pool": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "egn_broadcast_mul": (C.c_int, [_P, C.c_int, C.c_int, _P, _P, _P, _P]),
     "egn_knn_l2": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "egn_match_mutual": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
+    "egn_filter_points": (C.c_int, [_P, _P, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_float, _P, C.POINTER(C.c_int64), _P]),
     "egn_profile_enable": (C.c_int, [_P, C.c_int]),
     "egn_profile_read": (C.c_int, [_P, C.POINTER(ProfileEntry), C.c_int, C.POINTER(C.c_int), C.c_int]),
     "egn_launch_count": (C.c_int64, [_P]),

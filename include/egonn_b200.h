@@ -212,6 +212,24 @@ int egn_topk_smallest(const float *sigma, const int32_t *offsets, int n_batches,
 int egn_knn_l2(egn_ctx *ctx, const float *query, const float *map, int n_query, int n_map, int dim, int k, int32_t *idx_out,
                float *dist_out, egn_stream_t stream);
 
+/* ---- "next" rows: correspondences between the local descriptors of two clouds ------------------------
+ * Replaces: the feature-matching step inside eval/evaluate.py:381-399 (Open3D
+ * registration_ransac_based_on_feature_matching(..., mutual_filter=True): nearest neighbour in descriptor space, kept
+ * when mutual).  desc_a (n_a, dim), desc_b (n_b, dim) f32; idx_out (n_a) int32 = row of b matched to every row of a
+ * (-1: not mutual); dist_out (n_a) f32 Euclidean descriptor distance of the nearest neighbour, or NULL.  mutual = 0
+ * returns the plain nearest neighbour.  Ties: lower row.  RANSAC itself stays out of scope. */
+int egn_match_mutual(egn_ctx *ctx, const float *desc_a, const float *desc_b, int n_a, int n_b, int dim, int mutual, int32_t *idx_out,
+                     float *dist_out, egn_stream_t stream);
+
+/* ---- "next" rows: raw-scan ingest --------------------------------------------------------------------------
+ * Replaces: PointCloudLoader.__call__ misc/point_clouds.py:95-111 after read_pc (datasets/kitti/kitti_raw.py:16-22,
+ * datasets/mulran/mulran_raw.py:19-25: np.fromfile(...).reshape(-1, 4)[:, :3]).  records (n, stride) f32 with x, y, z in
+ * the first three floats (stride 4 for the .bin files, 3 for xyz arrays); remove_zero drops points with all |v| <= 1e-8
+ * (np.isclose(pc, 0)), remove_ground drops z <= ground_level (-1.5 KITTI, -0.9 MulRan); survivors keep their order.
+ * points_out (n,3) f32 caller-owned, *n_out = number of survivors (synchronises the stream once). */
+int egn_filter_points(egn_ctx *ctx, const float *records, int64_t n, int stride, int remove_zero, int remove_ground,
+                      float ground_level, float *points_out, int64_t *n_out, egn_stream_t stream);
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------------
  * egn_profile_enable(ctx, 1): every kernel class launched by this context is bracketed by CUDA events on its
  * stream and the pair counts needed for the algorithmic-byte model are computed at coords_build.
