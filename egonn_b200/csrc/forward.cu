@@ -80,13 +80,13 @@ size_t plan_floats(const Pyramid &py, const egn_net &net) {
     const size_t n = py.n[L] + 1;                          // + the zero row of pre-split maps
     f += n * net.down[L].cout + 3 * n * net.conv2[L].cout + (net.res[L].cin ? n * net.res[L].cout : 0) + 1024;
     f += 2 * n * net.conv2[L].cout;                        // fp32 copies for consumers that cannot read a pre-split map (rare)
-    f += (size_t)py.n_batches * (64 + 1) * net.conv2[L].cout + 128;
+    f += ((size_t)kNumSMs * 8 + 2 * (size_t)py.n_batches) * net.conv2[L].cout + 128;   // pooling partials (<= 8 CTAs per SM) + gates
   }
   f += head_floats(py, net.global_head) + head_floats(py, net.local_head);
   if (net.global_head.n_levels) {
     const size_t n = py.n[net.global_head.levels[0]];
     f += n * (net.global_mlp[0].cin ? net.global_mlp[0].cout + net.global_mlp[1].cout : 0) + 256;
-    f += (size_t)py.n_batches * 64 * 512 + 256;
+    f += ((size_t)kNumSMs * 8 + (size_t)py.n_batches) * 512 + 256;
   }
   if (net.local_head.n_levels) {
     const size_t n = py.n[net.local_head.levels[0]];

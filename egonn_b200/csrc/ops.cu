@@ -669,9 +669,12 @@ int op_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int 
   return run_conv(ctx, level_in, ksize, transposed, cin, cout, in, w, scale, shift, relu, accumulate, out, s);
 }
 
+// slices per cloud for the two-stage per-cloud reductions: ~256 rows per CTA, at most ~8 CTAs per SM in total - a single
+// 1M-point cloud (BASELINE config 5) gets as many CTAs as a batch of 16 scans
 static int pool_slices(int n_rows, int n_batches) {
-  int s = (int)div_up(n_rows, (int64_t)n_batches * 48);
-  return s < 1 ? 1 : (s > 64 ? 64 : s);
+  const int cap = std::max(1, (kNumSMs * 8) / std::max(1, n_batches));
+  int s = (int)div_up(n_rows, (int64_t)std::max(1, n_batches) * 256);
+  return s < 1 ? 1 : (s > cap ? cap : s);
 }
 
 // per-cloud pooling; part must hold n_batches*slices*c floats (taken from the feature arena by the caller)
