@@ -7,7 +7,7 @@ namespace egn {
 
 // ops.cu
 int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const float *scale, const float *shift, int cout,
-              int relu, const int *not_ones, int out_split, float *out, cudaStream_t s);
+              int relu, const int *not_ones, int out_split, float *out, cudaStream_t s, const void *wtc);
 int run_presplit_to_f32(egn_ctx *ctx, const float *in, int64_t floats, float *out, cudaStream_t s);
 int run_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const float *w,
              const float *scale, const float *shift, int relu, int accumulate, float *out, cudaStream_t s);
@@ -144,7 +144,8 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
   int *not_ones = ctx->dev_counts + P + 3;
   EGN_TRY(run_gather_rows1(ctx, features, py.perm0, py.n[0], f0, not_ones, s));
   EGN_TRY(run_conv0(ctx, net->conv0_ksize, f0, F.W(net->conv0.w), F.W(net->conv0.scale), F.W(net->conv0.shift),
-                    net->conv0.cout, 1, not_ones, x0.split, x0.p, s));
+                    net->conv0.cout, 1, not_ones, x0.split, x0.p, s,
+                    (ctx->use_tc && net->conv0.wtc >= 0 && net->conv0_ksize == 5) ? (const void *)(weights + net->conv0.wtc) : nullptr));
   tp.conv0 = x0.p;
   tp.conv0_split = x0.split;
   tp.c0 = net->conv0.cout;

@@ -590,8 +590,12 @@ __global__ void __launch_bounds__(kTopkThreads) k_topk_smallest(const float *__r
 // ------------------------------------------------------------------------------------------------------
 // host-side launchers
 // ------------------------------------------------------------------------------------------------------
+// conv0_tc.cu
+int run_conv0_tc(egn_ctx *ctx, const void *wpack, const float *scale, const float *shift, int relu, const int *not_ones, int out_split,
+                 float *out, double bytes, double flops, cudaStream_t s);
+
 int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const float *scale, const float *shift, int cout,
-              int relu, const int *not_ones, int out_split, float *out, cudaStream_t s) {
+              int relu, const int *not_ones, int out_split, float *out, cudaStream_t s, const void *wtc) {
   const Pyramid &py = ctx->pyr;
   EGN_CHECK(ksize == 5 || ksize == 3, EGN_ERR_INVALID, "conv0: kernel size %d not supported (3 or 5)", ksize);
   EGN_CHECK(cout == 32, EGN_ERR_INVALID, "conv0: %d output channels not supported (the egonn / MinkLoc3D stems use 32)", cout);
@@ -612,7 +616,9 @@ int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const fl
       EGN_CUDA(cudaFuncSetAttribute(k_conv0<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));          \
       attr = true;                                                                                                          \
     }                                                                                                                       \
-    if (not_ones)                                                                                                           \
+    if (not_ones && wtc && KS == 5)                                                                                         \
+      EGN_TRY(run_conv0_tc(ctx, wtc, scale, shift, relu, not_ones, out_split, out, bytes, flops, s));                       \
+    else if (not_ones)                                                                                                      \
       EGN_LAUNCH(ctx, NAME, bytes, flops, s,                                                                                \
                  k_conv0<KS, true><<<blocks1, C0<true>::kWarps * 32, smem1, s>>>(f0, py.keys[0], py.up[0], py.up[1], py.nbr[2], \
                                                                                  py.mask64, py.first0, n0, w, scale, shift, relu, not_ones, out_split, out)); \
@@ -656,7 +662,7 @@ int run_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int
     pairs = a.n_out;
   } else if (ksize == 5) {
     EGN_CHECK(level_in == 0 && cin == 1 && !accumulate, EGN_ERR_INVALID, "conv k=5 is supported at level 0 with cin=1 only");
-    return run_conv0(ctx, 5, in, w, scale, shift, cout, relu, nullptr, 0, out, s);
+    return run_conv0(ctx, 5, in, w, scale, shift, cout, relu, nullptr, 0, out, s, nullptr);
   } else {
     EGN_CHECK(false, EGN_ERR_INVALID, "conv: unsupported kernel size %d", ksize);
   }

@@ -38,7 +38,8 @@ def _bn_fold(sd, prefix, eps=1e-5):
 
 
 TC_SHAPES = {27: {(32, 32), (32, 64), (64, 64), (64, 128), (128, 128)}, 8: {(32, 32), (64, 64), (128, 128)},
-             1: {(32, 64), (64, 64), (64, 128), (128, 64), (128, 128)}}
+             1: {(32, 64), (64, 64), (64, 128), (128, 64), (128, 128)},
+             125: {(1, 32)}}          # conv0 5x5x5 with all-ones features: presence matrix x kernel (conv0_tc.cu)
 
 
 def pack_tc(kernel: torch.Tensor) -> torch.Tensor:
