@@ -363,10 +363,47 @@ __global__ void __launch_bounds__(256) k_pool_partial(const float *__restrict__ 
     *(float4 *)(part + ((size_t)b * slices + s) * c + 4 * threadIdx.x) = t;
   }
 }
-__global__ void k_pool_final(const float *__restrict__ part, const int *__restrict__ boff, int c, int slices, int mode, float p,
-                             float *__restrict__ out /* (B,c) */) {
+// sum (or max) of the per-slice partials of cloud b (c <= 256 channels): 256 threads = (256 / c) slice lanes x c channels, the
+// lanes are then combined in fixed order through shared memory (deterministic); result in s_tot[ch]
+__device__ __forceinline__ void reduce_slices(const float *__restrict__ part, int b, int c, int slices, bool is_max, float *s_tot /* [256] */) {
+  const int lanes = 256 / c;
+  const int ch = (int)threadIdx.x % c, l = (int)threadIdx.x / c;
+  float acc = is_max ? -INFINITY : 0.f;
+  if (l < lanes)
+    for (int s = l; s < slices; s += lanes) {
+      const float v = part[((size_t)b * slices + s) * c + ch];
+      acc = is_max ? fmaxf(acc, v) : acc + v;
+    }
+  s_tot[threadIdx.x] = acc;
+  __syncthreads();
+  if (l == 0) {
+    for (int j = 1; j < lanes; ++j) {
+      const float v = s_tot[j * c + ch];
+      acc = is_max ? fmaxf(acc, v) : acc + v;
+    }
+  }
+  __syncthreads();
+  if (l == 0) s_tot[ch] = acc;
+  __syncthreads();
+}
+__global__ void __launch_bounds__(256) k_pool_final(const float *__restrict__ part, const int *__restrict__ boff, int c, int slices, int mode,
+                                                    float p, float *__restrict__ out /* (B,c) */) {
+  __shared__ float s_tot[256];
   const int b = blockIdx.x;
   const int len = boff[b + 1] - boff[b];
+  if (c <= 256) {
+    reduce_slices(part, b, c, slices, mode == 2, s_tot);
+    if ((int)threadIdx.x < c) {
+      const float acc = s_tot[threadIdx.x];
+      float r;
+      if (len == 0) r = 0.f;
+      else if (mode == 0) r = acc / (float)len;
+      else if (mode == 1) r = powf(acc / (float)len, 1.0f / p);
+      else r = acc;
+      out[(size_t)b * c + threadIdx.x] = r;
+    }
+    return;
+  }
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     float acc = mode == 2 ? -INFINITY : 0.f;
     for (int s = 0; s < slices; ++s) {
@@ -381,20 +418,19 @@ __global__ void k_pool_final(const float *__restrict__ part, const int *__restri
     out[(size_t)b * c + ch] = r;
   }
 }
-// ECA gate (layers/eca_block.py:21-31): mean -> Conv1d(1,1,k, zero pad, no bias) over channels -> sigmoid
-__global__ void k_eca_gate(const float *__restrict__ part, const int *__restrict__ boff, int c, int slices,
-                           const float *__restrict__ wk, int k, float *__restrict__ gate /* (B,c) */) {
-  extern __shared__ float s_mean[];
+// ECA gate (layers/eca_block.py:21-31): mean -> Conv1d(1,1,k, zero pad, no bias) over channels -> sigmoid   (c <= 256)
+__global__ void __launch_bounds__(256) k_eca_gate(const float *__restrict__ part, const int *__restrict__ boff, int c, int slices,
+                                                  const float *__restrict__ wk, int k, float *__restrict__ gate /* (B,c) */) {
+  __shared__ float s_tot[256];
+  __shared__ float s_mean[256];
   const int b = blockIdx.x;
   const int len = boff[b + 1] - boff[b];
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
-    float acc = 0.f;
-    for (int s = 0; s < slices; ++s) acc += part[((size_t)b * slices + s) * c + ch];
-    s_mean[ch] = len ? acc / (float)len : 0.f;
-  }
+  reduce_slices(part, b, c, slices, false, s_tot);
+  if ((int)threadIdx.x < c) s_mean[threadIdx.x] = len ? s_tot[threadIdx.x] / (float)len : 0.f;
   __syncthreads();
   const int pad = (k - 1) / 2;
-  for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+  if ((int)threadIdx.x < c) {
+    const int ch = threadIdx.x;
     float y = 0.f;
     for (int j = 0; j < k; ++j) {
       const int cc = ch + j - pad;
@@ -693,7 +729,7 @@ int run_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, float p,
   EGN_LAUNCH(ctx, "global_pool", (double)py.n[level] * c * 4, 0, s,
              k_pool_partial<<<dim3(B, slices), 256, 0, s>>>(in, py.boff[level], c, slices, mode, p, eps, part));
   EGN_LAUNCH(ctx, "global_pool", (double)B * (slices + 1) * c * 4, 0, s,
-             k_pool_final<<<B, threads, 0, s>>>(part, py.boff[level], c, slices, mode, p, out));
+             k_pool_final<<<B, 256, 0, s>>>(part, py.boff[level], c, slices, mode, p, out));
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
 }
@@ -851,8 +887,9 @@ int run_eca_gate(egn_ctx *ctx, int level, int c, const float *t, const float *wk
   EGN_CHECK((c & 3) == 0 && c <= 1024, EGN_ERR_INVALID, "eca: channels must be a multiple of 4 (<= 1024)");
   EGN_LAUNCH(ctx, "eca_pool", (double)py.n[level] * c * 4, 0, s,
              k_pool_partial<<<dim3(py.n_batches, slices), 256, 0, s>>>(t, py.boff[level], c, slices, 0, 1.f, 0.f, part));
+  EGN_CHECK(c <= 256, EGN_ERR_INVALID, "eca: at most 256 channels");
   EGN_LAUNCH(ctx, "eca_gate", (double)py.n_batches * (slices + 1) * c * 4, 0, s,
-             k_eca_gate<<<py.n_batches, threads, (size_t)c * 4, s>>>(part, py.boff[level], c, slices, wk, k, gate));
+             k_eca_gate<<<py.n_batches, 256, 0, s>>>(part, py.boff[level], c, slices, wk, k, gate));
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
 }
