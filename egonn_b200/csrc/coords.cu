@@ -23,9 +23,39 @@ constexpr int kTile = kTileThreads * kTileSteps;               // 2048 keys per 
 constexpr int kWarpsPerTile = kTileThreads / 32;
 
 // ------------------------------------------------------------------------------------------------------
+// Narrow sort keys.  The radix sort is the one multi-pass step of the build and its cost is the number of 8-bit passes
+// (CUB onesweep: ~15 us per pass at 0.75 M keys, look-back latency).  A level-0 key has 54 Morton bits because the
+// coordinate bias is 2^17; real scans span a few thousand voxels.  When every |c| < 2^11 the key
+//     compact = batch << 36 | morton36(c + 2^11)
+// is ORDER-EQUIVALENT to the full key (adding 2^17 - 2^11 maps the top bit h of c + 2^11 to the constant patterns 0111111 /
+// 1000000 in bits 11..17 and leaves the low 11 bits: the most significant differing bit of two keys moves from bit 11 to
+// bit 17 on the same axes with the same sign), so sorting 36 + batch bits (5-6 passes instead of 8) gives the same
+// permutation; k_expand_keys rebuilds the full keys afterwards.  The pack kernels flag (status bit 1) any coordinate
+// outside the narrow range and the build is then redone with full-width keys.
+// ------------------------------------------------------------------------------------------------------
+constexpr int kNarrowBits = 12;                                  // per-axis bits of the compact key
+constexpr int kNarrowBias = 1 << (kNarrowBits - 1);
+__device__ __forceinline__ uint64_t make_narrow_key(uint32_t b, int cx, int cy, int cz) {
+  return ((uint64_t)b << (3 * kNarrowBits)) | spread3((uint32_t)(cx + kNarrowBias)) | (spread3((uint32_t)(cy + kNarrowBias)) << 1) |
+         (spread3((uint32_t)(cz + kNarrowBias)) << 2);
+}
+__device__ __forceinline__ bool narrow_ok(int cx, int cy, int cz) {
+  return cx >= -kNarrowBias && cx < kNarrowBias && cy >= -kNarrowBias && cy < kNarrowBias && cz >= -kNarrowBias && cz < kNarrowBias;
+}
+__global__ void k_expand_keys(uint64_t *__restrict__ keys, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t k = keys[i];
+    const uint32_t b = (uint32_t)(k >> (3 * kNarrowBits));
+    const uint64_t m = k & ((1ull << (3 * kNarrowBits)) - 1ull);
+    const uint32_t d = (uint32_t)(kAxisBias - kNarrowBias);
+    keys[i] = make_key(0, b, compact3(m) + d, compact3(m >> 1) + d, compact3(m >> 2) + d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
 // pack (b,x,y,z) -> key, validate
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_pack_keys(const int4 *__restrict__ coords, int n, uint64_t *__restrict__ keys,
+__global__ void k_pack_keys(const int4 *__restrict__ coords, int n, int narrow, uint64_t *__restrict__ keys,
                             uint32_t *__restrict__ vals, int *__restrict__ dev_counts /* [P]=n_batches, [P+1]=status */) {
   int bmax = 0, bad = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -37,15 +67,20 @@ __global__ void k_pack_keys(const int4 *__restrict__ coords, int n, uint64_t *__
       c = make_int4(0, 0, 0, 0);
     }
     bmax = max(bmax, c.x + 1);
-    keys[i] = make_key(0, (uint32_t)c.x, (uint32_t)(c.y + kAxisBias), (uint32_t)(c.z + kAxisBias),
-                       (uint32_t)(c.w + kAxisBias));
+    if (narrow) {
+      if (!narrow_ok(c.y, c.z, c.w)) { bad |= 2; c.y = c.z = c.w = 0; }          // outside the narrow range: the build is redone
+      keys[i] = make_narrow_key((uint32_t)c.x, c.y, c.z, c.w);
+    } else {
+      keys[i] = make_key(0, (uint32_t)c.x, (uint32_t)(c.y + kAxisBias), (uint32_t)(c.z + kAxisBias),
+                         (uint32_t)(c.w + kAxisBias));
+    }
     vals[i] = (uint32_t)i;
   }
   bmax = __reduce_max_sync(0xffffffffu, bmax);
-  bad = __reduce_max_sync(0xffffffffu, bad);
+  bad = __reduce_or_sync(0xffffffffu, bad);
   if ((threadIdx.x & 31) == 0) {
     if (bmax) atomicMax(&dev_counts[P], bmax);
-    if (bad) atomicOr(&dev_counts[P + 1], 1);
+    if (bad) atomicOr(&dev_counts[P + 1], bad);
   }
 }
 
@@ -332,7 +367,7 @@ static size_t sort_scratch_bytes(int64_t n) {
 }
 
 __global__ void k_quant_pack_batch(const float *__restrict__ pts, int n, const int *__restrict__ cloud_off, int n_clouds, float q0,
-                                   float q1, float q2, int polar, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                   float q1, float q2, int polar, int narrow, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
                                    int *__restrict__ dev_counts);
 
 struct BuildSource {
@@ -344,7 +379,7 @@ struct BuildSource {
   int polar = 0;
 };
 
-static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64, egn_coords_info *info, cudaStream_t s);
+static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64, egn_coords_info *info, cudaStream_t s, bool narrow = true);
 
 int coords_build(egn_ctx *ctx, const int32_t *coords, int64_t n64, egn_coords_info *info, cudaStream_t s) {
   EGN_CHECK(ctx && coords && info, EGN_ERR_INVALID, "coords_build: null argument");
@@ -365,7 +400,7 @@ int coords_build_points(egn_ctx *ctx, const float *points, int64_t n64, const in
   return coords_build_common(ctx, src, n64, info, s);
 }
 
-static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64, egn_coords_info *info, cudaStream_t s) {
+static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64, egn_coords_info *info, cudaStream_t s, bool narrow) {
   EGN_CHECK(n64 > 0 && n64 < (int64_t)1 << 26, EGN_ERR_INVALID, "coords_build: n=%lld out of range (1..2^26)", (long long)n64);
   const int n = (int)n64;
   Pyramid &py = ctx->pyr;
@@ -382,25 +417,32 @@ static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64
   EGN_CUDA(cudaMemsetAsync(ctx->dev_counts, 0, sizeof(HostCounts), s));
   if (src.coords)
     EGN_LAUNCH(ctx, "coords_pack_keys", (double)n * 28, 0, s,
-               k_pack_keys<<<grid_for(n, 256), 256, 0, s>>>((const int4 *)src.coords, n, kin, vin, ctx->dev_counts));
+               k_pack_keys<<<grid_for(n, 256), 256, 0, s>>>((const int4 *)src.coords, n, narrow ? 1 : 0, kin, vin, ctx->dev_counts));
   else
     EGN_LAUNCH(ctx, "quantize_pack_batch", (double)n * 24, 0, s,
                k_quant_pack_batch<<<grid_for(n, 256), 256, 0, s>>>(src.points, n, src.cloud_off, src.n_clouds, src.step[0], src.step[1],
-                                                                  src.step[2], src.polar, kin, vin, ctx->dev_counts));
-  if (ctx->prof.on) ctx->prof.begin("coords_radix_sort(cub)", (double)n * 24 * 8, 0, s);
-  EGN_TRY(sort_pairs(sc, kin, kout, vin, vout, n, 64, s));
+                                                                  src.step[2], src.polar, narrow ? 1 : 0, kin, vin, ctx->dev_counts));
+  // sorted bits: full key = 64; narrow key = 36 Morton bits + the batch bits (known on the host for the point path)
+  int batch_bits = 10;
+  if (src.points) { batch_bits = 1; while ((1 << batch_bits) < src.n_clouds) ++batch_bits; }
+  const int end_bit = narrow ? 3 * kNarrowBits + batch_bits : 64;
+  if (ctx->prof.on) ctx->prof.begin("coords_radix_sort(cub)", (double)n * 24 * ((end_bit + 7) / 8), 0, s);
+  EGN_TRY(sort_pairs(sc, kin, kout, vin, vout, n, end_bit, s));
   if (ctx->prof.on) ctx->prof.end(s);
+  if (narrow) EGN_LAUNCH(ctx, "coords_expand_keys", (double)n * 16, 0, s, k_expand_keys<<<grid_for(n, 256), 256, 0, s>>>(kout, n));
   EGN_LAUNCH(ctx, "coords_level_count", (double)n * 8, 0, s, k_level_count<<<nblocks, kTileThreads, 0, s>>>(kout, n, nblocks, counts));
   EGN_LAUNCH(ctx, "coords_level_scan", (double)nblocks * P * 8, 0, s, k_level_scan<<<1, 1024, 0, s>>>(counts, nblocks, ctx->dev_counts));
   EGN_CUDA(cudaMemcpyAsync(ctx->host, ctx->dev_counts, sizeof(HostCounts), cudaMemcpyDeviceToHost, s));
   EGN_CUDA(cudaStreamSynchronize(s));
 
   const HostCounts &hc = *ctx->host;
+  if (narrow && (hc.status & 2) && !(hc.status & 1))          // some coordinate outside the narrow-key range: full-width keys
+    return coords_build_common(ctx, src, n64, info, s, false);
   info->n_input = n;
   info->n_batches = hc.n_batches;
-  info->status = hc.status ? EGN_ERR_RANGE : EGN_OK;
+  info->status = (hc.status & 1) ? EGN_ERR_RANGE : EGN_OK;
   for (int L = 0; L < P; ++L) info->n_rows[L] = hc.totals[L];
-  EGN_CHECK(hc.status == 0, EGN_ERR_RANGE,
+  EGN_CHECK((hc.status & 1) == 0, EGN_ERR_RANGE,
             "coords_build: coordinate outside [-2^17, 2^17) (or NaN point) or batch index outside [0, 1023)");
 
   // exact-size pyramid storage
@@ -529,7 +571,7 @@ __global__ void k_quant_pack(const float *__restrict__ pts, int n, float q0, flo
 // fused path: raw points of B concatenated clouds -> level-0 keys (batch | Morton(voxel)) in one pass; the cloud of a
 // point comes from a binary search in the (B+1) point offsets.  Same arithmetic as k_quant_pack.
 __global__ void k_quant_pack_batch(const float *__restrict__ pts, int n, const int *__restrict__ cloud_off, int n_clouds, float q0,
-                                   float q1, float q2, int polar, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                   float q1, float q2, int polar, int narrow, uint64_t *__restrict__ keys, uint32_t *__restrict__ vals,
                                    int *__restrict__ dev_counts) {
   int bad = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -553,12 +595,17 @@ __global__ void k_quant_pack_batch(const float *__restrict__ pts, int n, const i
     const float lim = (float)kAxisBias;
     const bool ok = fa >= -lim && fa < lim && fb >= -lim && fb < lim && fc >= -lim && fc < lim;
     int ia = 0, ib = 0, ic = 0;
-    if (ok) { ia = (int)fa; ib = (int)fb; ic = (int)fc; } else bad = 1;
-    keys[i] = make_key(0, (uint32_t)lo, (uint32_t)(ia + kAxisBias), (uint32_t)(ib + kAxisBias), (uint32_t)(ic + kAxisBias));
+    if (ok) { ia = (int)fa; ib = (int)fb; ic = (int)fc; } else bad |= 1;
+    if (narrow) {
+      if (!narrow_ok(ia, ib, ic)) { bad |= 2; ia = ib = ic = 0; }
+      keys[i] = make_narrow_key((uint32_t)lo, ia, ib, ic);
+    } else {
+      keys[i] = make_key(0, (uint32_t)lo, (uint32_t)(ia + kAxisBias), (uint32_t)(ib + kAxisBias), (uint32_t)(ic + kAxisBias));
+    }
     vals[i] = (uint32_t)i;
   }
-  bad = __reduce_max_sync(0xffffffffu, bad);
-  if ((threadIdx.x & 31) == 0 && bad) atomicOr(&dev_counts[P + 1], 1);
+  bad = __reduce_or_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicOr(&dev_counts[P + 1], bad);
   if (blockIdx.x == 0 && threadIdx.x == 0) dev_counts[P] = n_clouds;
 }
 
