@@ -80,6 +80,7 @@ struct egn_ctx {
   size_t win_bytes = 0;
   unsigned hint_producer = 20000, hint_single = 20000;   // mbarrier try_wait suspend hints (EGN_HINT_P / EGN_HINT_S)
   void *trace = nullptr;            // debug timeline buffer for k_sconv_tc (EGN_TRACE=1 allocates 64*8 int64)
+  int nsplit_max = 74;              // N-split 128-channel convolutions up to this many row tiles (EGN_NSPLIT_MAX)
   bool ksplit = false;              // K-split of small 128-channel levels (EGN_KSPLIT=1)
   void *splitk_buf = nullptr;       // raw partial tiles of K-split convolutions (small levels only)
   size_t splitk_cap = 0;

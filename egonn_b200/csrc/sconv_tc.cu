@@ -408,7 +408,7 @@ int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, 
   // scratch arena and k_splitk_finish adds them in fixed order and applies the BatchNorm/ReLU epilogue (deterministic).
   if (cin == 128 && cout == 128 && (ksize == 3 || ksize == 2) && !accumulate) {
     const int tiles = (int)div_up(a.n_out, tc::kRows);
-    if (tiles <= 74) {        // N = 32 -> <= 148 CTAs for <= 37 tiles; N = 64 -> <= 148 CTAs for <= 74 tiles
+    if (tiles <= ctx->nsplit_max) {   // N = 32 -> <= 148 CTAs for <= 37 tiles; N = 64 -> <= 148 CTAs for <= 74 tiles (2 CTAs/SM beyond)
       const int splits = (!ctx->ksplit || out_split) ? 1 : (ksize == 3 ? (tiles <= 37 ? 3 : 1) : 1);
       tc::Args b = a;
       float *part = nullptr;
