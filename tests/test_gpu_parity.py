@@ -360,3 +360,43 @@ def test_global_descriptor_retrieval_matches_numpy(cuda):
         assert np.array_equal(got, exp) or np.allclose(d[got], d[exp], rtol=1e-6)
         np.testing.assert_allclose(dist[i].cpu().numpy(), d[exp], rtol=1e-5)
     assert idx[0, 0] == 5 and idx[1, 0] == 17
+
+
+@pytest.mark.parametrize("n_vox", [1, 2, 7, 130])
+def test_tiny_clouds_vs_oracle(n_vox, cuda, weights):
+    """Edge sizes: a handful of voxels (every pyramid level has >= 1 row, tiles are mostly padding), incl. a row count just
+    over one 128-row tile."""
+    quant = GOLDEN_CASES["cfg1_cartesian"]
+    rng = np.random.default_rng(n_vox)
+    c = np.unique(rng.integers(-6, 6, size=(4 * n_vox, 3)), axis=0)[:n_vox].astype(np.int32)
+    coords = np.concatenate([np.zeros((c.shape[0], 1), np.int32), c], axis=1)
+    feats = torch.ones((coords.shape[0], 1))
+    ref = egonn_oracle.forward(weights, coords, feats, quant)
+    model, _ = _model(weights, quant, cuda)
+    p = model.forward_packed({"coords": torch.from_numpy(coords).to(cuda), "features": feats.to(cuda)})
+    o = lex_order(p["local_coords"])
+    assert np.array_equal(p["local_coords"].cpu().numpy()[o], ref["coords_L3"])
+    assert_close_rel(p["global"], ref["global"], RTOL, "global")
+    assert_close_rel(p["descriptors"][o], ref["descriptors"], RTOL, "descriptors")
+    assert_close_rel(p["keypoints"][o], ref["keypoints"], RTOL, "keypoints")
+    assert_close_rel(p["sigma"][o], ref["sigma"], RTOL, "sigma")
+
+
+def test_batch_with_an_empty_cloud(cuda, weights):
+    """Batch indices {0, 2}: cloud 1 has no voxel.  The other clouds are unaffected and cloud 1's global descriptor is 0."""
+    g = load_golden("mini3_cartesian")
+    quant = GOLDEN_CASES["mini3_cartesian"]
+    model, _ = _model(weights, quant, cuda)
+    coords = torch.from_numpy(g["coords"]).to(cuda)
+    keep = coords[:, 0] != 1
+    sub = coords[keep]
+    full = model.forward_packed({"coords": coords, "features": torch.ones((coords.shape[0], 1), device=cuda)})
+    part = model.forward_packed({"coords": sub, "features": torch.ones((sub.shape[0], 1), device=cuda)})
+    assert part["global"].shape[0] == 3 and torch.isfinite(part["global"]).all()
+    assert torch.all(part["global"][1] == 0)
+    for b in (0, 2):
+        assert_close_rel(part["global"][b], full["global"][b], 5e-5, f"global of cloud {b}")
+    lo, lp = full["local_offsets"].long(), part["local_offsets"].long()
+    assert lp[2] == lp[1]                                             # no local rows for the empty cloud
+    for b in (0, 2):
+        assert_close_rel(part["descriptors"][lp[b]:lp[b + 1]], full["descriptors"][lo[b]:lo[b + 1]], 5e-5, f"descriptors of cloud {b}")
