@@ -123,7 +123,6 @@ int egn_ctx_create(egn_ctx **out, int device) {
   const char *ks = getenv("EGN_KSPLIT");
   ctx->ksplit = ks && ks[0] == '1';
   if (const char *t = getenv("EGN_TRACE")) if (t[0] == '1') { cudaMalloc(&ctx->trace, 64 * 8 * 8); cudaMemset(ctx->trace, 0, 64 * 8 * 8); }
-  if (const char *v = getenv("EGN_TC_VARIANT")) ctx->tc_variant = atoi(v);
   if (const char *v = getenv("EGN_NSPLIT_MAX")) ctx->nsplit_max = atoi(v);
   if (const char *h = getenv("EGN_HINT_P")) ctx->hint_producer = (unsigned)atoi(h);
   if (const char *h = getenv("EGN_HINT_S")) ctx->hint_single = (unsigned)atoi(h);

@@ -73,7 +73,6 @@ struct egn_ctx {
   egn::Taps taps;
   egn::Prof prof;
   bool use_tc = true;
-  int tc_variant = 1;               // tensor-core convolution kernels: 1 = A operand in tensor memory (sconv_ts.cu), 0 = A staged in shared memory (sconv_tc.cu)
   cudaStream_t aux = nullptr;       // second stream: the local head overlaps the upper trunk levels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   const void *win_ptr = nullptr;    // persisting-L2 window over the weight blob (egn_weights_resident)

@@ -46,7 +46,7 @@ struct Fwd {
     return ctx->use_tc && l.wtc >= 0 && sconv_tc_supported(ksize, transposed, l.cin, l.cout);
   }
   // may a map whose main consumer is layer l be stored pre-split?
-  bool want_split(const egn_layer &l, int ksize, int transposed) const { return ctx->tc_variant == 1 && tc_ok(l, ksize, transposed); }
+  bool want_split(const egn_layer &l, int ksize, int transposed) const { return tc_ok(l, ksize, transposed); }
 
   // conv described by an egn_layer on the pyramid
   int layer(const egn_layer &l, int level_in, int ksize, int transposed, Map in, int relu, int accumulate, Map out) {

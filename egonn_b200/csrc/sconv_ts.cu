@@ -2,7 +2,7 @@
 //
 //   out[o, :] = epilogue( sum_k  in[nbr(o,k), :] @ W[k] )          (MinkowskiConvolution forward)
 //
-// Why: in k_sconv_tc (sconv_tc.cu) every 64-element chunk of the gathered operand is written to shared memory as
+// Why: in the first-generation kernel (k_sconv_tc, see sconv_tc.cu's header) every 64-element chunk of the gathered operand is written to shared memory as
 // two bf16 images (32 KB of STS) and then read three times by tcgen05.mma (hi*hi, lo*hi, hi*lo: 48 KB) - the
 // shared-memory port and the instructions that feed it, not HBM and not the tensor pipe, bound the kernel
 // (profiles/r01_tc_kernel_stalls.md).  tcgen05.mma can take A from tensor memory ("TS" form), and tcgen05.st writes
@@ -17,7 +17,9 @@
 //                 FP32 accumulators in TMEM columns [0, COUT); tcgen05.commit frees the stage.
 //   * epilogue  : tcgen05.ld -> folded BatchNorm scale/shift (+ReLU, +accumulate) -> the output row, written once.
 // TMEM plan: COUT == 128: 1 CTA/SM, 512 columns = 128 accumulator + 6 stages x 64; otherwise 2 CTAs/SM, 256 columns
-// each = 64 accumulator + 3 stages x 64.  Same numerics as k_sconv_tc (bf16x3 split, FP32 accumulation).
+// each = 64 accumulator + 3 stages x 64.  bf16x3 split (hi*hi + lo*hi + hi*lo), FP32 accumulation.
+// Gathers are 256-bit loads: lane j4 of a row reads channels 8*j4 .. 8*j4+7 of each 32-channel block, one L1 wavefront per
+// 128-byte line; the weight image carries the matching K permutation (weights.py: _perm32).
 #include "ctx.cuh"
 #include "tc_ptx.cuh"
 
@@ -166,20 +168,17 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
 #pragma unroll
           for (int rs = 0; rs < 2; ++rs) {
             const int *nb = nb_base + (16 * hf + 8 * rs) * KOFF;
+            // lane j4 reads channels 8*j4 .. 8*j4+7 of each 32-channel block with one 256-bit load (weights.py: _perm32)
             if (CIN == 32) {
               const int k0 = 2 * jc, k1 = 2 * jc + 1;
               const int s0 = nb[k0], s1 = k1 < KOFF ? nb[k1] : a.zero_row;
-              const uint4 *p0 = reinterpret_cast<const uint4 *>(a.in + (size_t)s0 * CIN) + j4;
-              const uint4 *p1 = reinterpret_cast<const uint4 *>(a.in + (size_t)s1 * CIN) + j4;
-              v[hf][rs][0] = __ldg(p0);
-              v[hf][rs][1] = __ldg(p0 + 4);
-              v[hf][rs][2] = __ldg(p1);
-              v[hf][rs][3] = __ldg(p1 + 4);
+              ldg256(a.in + (size_t)s0 * CIN + 8 * j4, v[hf][rs][0], v[hf][rs][1]);
+              ldg256(a.in + (size_t)s1 * CIN + 8 * j4, v[hf][rs][2], v[hf][rs][3]);
             } else {
               const int k = CIN == 64 ? jc : (jc >> 1);
-              const uint4 *p0 = reinterpret_cast<const uint4 *>(a.in + (size_t)nb[k] * CIN + (CIN == 128 ? (jc & 1) * 64 : 0)) + j4;
-#pragma unroll
-              for (int m = 0; m < 4; ++m) v[hf][rs][m] = __ldg(p0 + 4 * m);
+              const float *p0 = a.in + (size_t)nb[k] * CIN + (CIN == 128 ? (jc & 1) * 64 : 0) + 8 * j4;
+              ldg256(p0, v[hf][rs][0], v[hf][rs][1]);
+              ldg256(p0 + 32, v[hf][rs][2], v[hf][rs][3]);
             }
           }
         if (tr) a.trace[i * 8 + 4] = clock64();
@@ -209,18 +208,14 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
             if (CIN == 32) {
               const int k0 = 2 * jc, k1 = 2 * jc + 1;
               const int s0 = nb[k0], s1 = k1 < KOFF ? nb[k1] : -1;
-              const float *p0 = a.in + (size_t)(s0 >= 0 ? s0 : 0) * CIN + 4 * j4;
-              const float *p1 = a.in + (size_t)(s1 >= 0 ? s1 : 0) * CIN + 4 * j4;
-              ldg4_pred(p0, s0 >= 0, v[hf][rs][0]);
-              ldg4_pred(p0 + 16, s0 >= 0, v[hf][rs][1]);
-              ldg4_pred(p1, s1 >= 0, v[hf][rs][2]);
-              ldg4_pred(p1 + 16, s1 >= 0, v[hf][rs][3]);
+              ldg256_pred(a.in + (size_t)(s0 >= 0 ? s0 : 0) * CIN + 8 * j4, s0 >= 0, v[hf][rs][0], v[hf][rs][1]);
+              ldg256_pred(a.in + (size_t)(s1 >= 0 ? s1 : 0) * CIN + 8 * j4, s1 >= 0, v[hf][rs][2], v[hf][rs][3]);
             } else {
               const int k = CIN == 64 ? jc : (jc >> 1);
               const int s0 = nb[k];
-              const float *p0 = a.in + (size_t)(s0 >= 0 ? s0 : 0) * CIN + (CIN == 128 ? (jc & 1) * 64 : 0) + 4 * j4;
-#pragma unroll
-              for (int m = 0; m < 4; ++m) ldg4_pred(p0 + 16 * m, s0 >= 0, v[hf][rs][m]);
+              const float *p0 = a.in + (size_t)(s0 >= 0 ? s0 : 0) * CIN + (CIN == 128 ? (jc & 1) * 64 : 0) + 8 * j4;
+              ldg256_pred(p0, s0 >= 0, v[hf][rs][0], v[hf][rs][1]);
+              ldg256_pred(p0 + 32, s0 >= 0, v[hf][rs][2], v[hf][rs][3]);
             }
           }
         mbar_wait(&empty[s], ph ^ 1u, a.hint_producer);

@@ -181,6 +181,26 @@ __device__ __forceinline__ void ldg4_pred(const float *p, bool pred, float4 &a) 
       : "l"(p), "r"((uint32_t)pred));
 }
 
+// 256-bit global loads (sm_100: LDG.E.256): 32 contiguous bytes per lane -> the four lanes of a row cover a whole 128-byte
+// line with ONE wavefront.  The address must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const void *p, uint4 &a, uint4 &b) {
+  asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(p));
+}
+__device__ __forceinline__ void ldg256_pred(const float *p, bool pred, float4 &a, float4 &b) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %9, 0;\n\t"
+      "mov.b32 %0, 0; mov.b32 %1, 0; mov.b32 %2, 0; mov.b32 %3, 0;\n\t"
+      "mov.b32 %4, 0; mov.b32 %5, 0; mov.b32 %6, 0; mov.b32 %7, 0;\n\t"
+      "@q ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\t"
+      "}"
+      : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+      : "l"(p), "r"((uint32_t)pred));
+}
+
 // ---- pre-split feature maps ---------------------------------------------------------------------------------------------
 // A feature map that only tensor-core convolutions gather from is stored PRE-SPLIT: same (n, C) x 4-byte footprint as
 // fp32, but every group of 4 channels is the 16 bytes [hi0 hi1 hi2 hi3 | lo0 lo1 lo2 lo3] (bf16; x = hi + lo to 2^-17

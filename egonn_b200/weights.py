@@ -42,13 +42,27 @@ TC_SHAPES = {27: {(32, 32), (32, 64), (64, 64), (64, 128), (128, 128)}, 8: {(32,
              125: {(1, 32)}}          # conv0 5x5x5 with all-ones features: presence matrix x kernel (conv0_tc.cu)
 
 
-def pack_tc(kernel: torch.Tensor) -> torch.Tensor:
+def _perm32() -> torch.Tensor:
+    """K position p = 16*mm + 4*j + e (mm in 0..1, j in 0..3, e in 0..3) of a 32-channel block holds channel 8*j + 4*mm + e:
+    the four lanes that feed one row of tcgen05.st.16x256b then read the row's 128-byte line as four contiguous 32-byte
+    pieces (one 256-bit load each, one L1 wavefront per line) instead of eight 16-byte pieces in two instructions."""
+    p = torch.arange(32)
+    mm, j, e = p // 16, (p % 16) // 4, p % 4
+    return 8 * j + 4 * mm + e
+
+
+def pack_tc(kernel: torch.Tensor, perm32: Optional[bool] = None) -> torch.Tensor:
     """(K, Cin, Cout) f32 kernel -> the tensor-core image of ``egn_conv_tc`` as a flat bf16 tensor:
     [ceil(K*Cin/64)][hi|lo][Cout][64] with the 16-byte groups of row n XOR-swizzled by (n & 7) - byte for byte the
     SWIZZLE_128B K-major shared-memory tile that ``tcgen05.mma`` reads, so the kernel fetches a chunk with one
     bulk copy.  hi = bf16(w), lo = bf16(w - hi): w ~ hi + lo to 2^-17 relative."""
     K, cin, cout = kernel.shape
     flat = kernel.detach().to(torch.float32).cpu().reshape(K * cin, cout)
+    if perm32 is None:
+        perm32 = cin % 32 == 0                                                # gathered feature rows; conv0's offset axis stays natural
+    if perm32:
+        assert cin % 32 == 0
+        flat = flat.reshape(-1, 32, cout)[:, _perm32(), :].reshape(K * cin, cout)
     nch = (K * cin + 63) // 64
     pad = nch * 64 - K * cin
     if pad:

@@ -205,8 +205,9 @@ def test_batch_independence_and_heads_switches(cuda, weights):
     one = coords[sel].clone()
     one[:, 0] = 0
     single = model({"coords": one, "features": feats[sel]})
-    assert_close_rel(single["global"][0], full["global"][1], 1e-5, "global of cloud 1 alone")
-    assert_close_rel(single["descriptors"][0], full["descriptors"][1], 1e-5, "descriptors of cloud 1 alone")
+    # not bit-identical: the slice partition of the per-cloud pooling sums depends on the batch composition
+    assert_close_rel(single["global"][0], full["global"][1], 5e-5, "global of cloud 1 alone")
+    assert_close_rel(single["descriptors"][0], full["descriptors"][1], 5e-5, "descriptors of cloud 1 alone")
     y = model({"coords": coords, "features": feats}, disable_local_head=True)
     assert set(y) == {"global"}
     y = model({"coords": coords, "features": feats}, disable_global_head=True)

@@ -29,6 +29,11 @@ def test_pack_tc_is_a_swizzled_hi_lo_split():
         assert img.dtype == torch.bfloat16 and img.numel() == ((K * cin + 63) // 64) * 2 * cout * 64
         hi, lo = _unpack_tc(img, K, cin, cout)
         flat = w.reshape(K * cin, cout)
+        if cin % 32 == 0:      # gathered feature rows: K position 16*mm + 4*j + e of every 32-channel block holds channel 8*j + 4*mm + e
+            p = torch.arange(32)
+            perm = 8 * ((p % 16) // 4) + 4 * (p // 16) + p % 4
+            assert sorted(perm.tolist()) == list(range(32))
+            flat = flat.reshape(-1, 32, cout)[:, perm, :].reshape(K * cin, cout)
         assert torch.equal(hi, flat.to(torch.bfloat16).float())                       # hi = bf16(w)
         assert torch.equal(lo, (flat - hi).to(torch.bfloat16).float())                # lo = bf16(w - hi)
         assert float(((hi + lo) - flat).abs().max() / flat.abs().max()) < 2.0 ** -16  # w ~ hi + lo
