@@ -714,7 +714,7 @@ int op_conv(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int 
 // slices per cloud for the two-stage per-cloud reductions: ~48 rows per CTA, at most ~8 CTAs per SM in total - a single
 // 1M-point cloud (BASELINE config 5) gets as many CTAs as a batch of 16 scans
 static int pool_slices(int n_rows, int n_batches) {
-  const int cap = std::max(1, (kNumSMs * 8) / std::max(1, n_batches));
+  const int cap = std::max(1, std::min(256, (kNumSMs * 8) / std::max(1, n_batches)));   // <= 256: the second stage walks them per cloud
   int s = (int)div_up(n_rows, (int64_t)std::max(1, n_batches) * 48);
   return s < 1 ? 1 : (s > cap ? cap : s);
 }
