@@ -1,6 +1,6 @@
 """Dump the clock64 timeline of one mid-grid CTA of a tensor-core convolution (EGN_TRACE=1; k_sconv_ts stamps).
 
-    python tools/trace_conv.py LEVEL CHANNELS [split]     # split: feed a pre-split input map (the engine-internal format)
+    python tools/trace_conv.py LEVEL CHANNELS             # one isolated 3x3x3 convolution at a cfg2 level, fp32 input map
 """
 import ctypes as C
 import os
