@@ -1,5 +1,7 @@
-"""-m gpu parity at BASELINE.json's FULL sizes (cfg2 B=16, cfg3 B=64, cfg4 B=256, cfg5 1M points), where the CPU
-oracle would take minutes per cloud: size-independent properties of the domain instead of an element-wise diff.
+"""-m gpu parity at BASELINE.json's FULL BATCH sizes (cfg2 B=16, cfg3 B=64, cfg4 B=256, cfg5 1M points): size-independent
+properties of the domain over the WHOLE batch.  The element-wise diff against the CPU oracle at these sizes (1-3 s of
+oracle time per cloud, ~1.5 min for cfg5) is tests/test_gpu_oracle_fullsize.py; the properties here cover all clouds of
+the batch, which the oracle (16-256 clouds x seconds) would make slow.
 
   * coordinate maps   : level-L map == unique(floor(c / 2^L) * 2^L) computed independently with torch ops on the
                         device (bit-exact, keyed by coordinate), batch offsets partition the rows
