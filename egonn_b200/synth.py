@@ -37,17 +37,27 @@ def uniform_cloud(n: int, seed: int) -> np.ndarray:
 
 def spinning_lidar_cloud(seed: int, beams: int = 64, azimuths: int = 2083, elev=(-24.8, 2.0),
                          height: float = 1.73, max_range: float = 80.0, n_cylinders: int = 120,
-                         noise: float = 0.02) -> np.ndarray:
+                         noise: float = 0.02, pose=None, noise_seed=None) -> np.ndarray:
     """One revolution of a ``beams`` x ``azimuths`` scanner at ``height`` m above a ground plane, ray-cast
     against ~n_cylinders random vertical cylinders (trunks, poles, cars as fat cylinders) and two
-    street walls; Gaussian range noise; misses dropped.  Returns (N,3) float32 in the sensor frame."""
+    street walls; Gaussian range noise; misses dropped.  Returns (N,3) float32 in the sensor frame.
+
+    ``pose = (px, py, yaw)`` re-scans the SAME scene (the one ``seed`` draws) from a sensor displaced by (px, py) m
+    and rotated by yaw rad - a "revisit"; ``noise_seed`` then draws independent range noise.  The defaults leave the
+    generated clouds bit-identical to the pose-free generator the golden vectors and bench workloads were made with."""
     rng = np.random.default_rng(seed)
     el = np.deg2rad(np.linspace(elev[0], elev[1], beams))
     az = np.linspace(-np.pi, np.pi, azimuths, endpoint=False) + rng.uniform(0, 2 * np.pi / azimuths)
     ce, se = np.cos(el)[:, None], np.sin(el)[:, None]
-    dx = (ce * np.cos(az)[None, :]).ravel()
-    dy = (ce * np.sin(az)[None, :]).ravel()
+    sdx = (ce * np.cos(az)[None, :]).ravel()          # ray directions in the SENSOR frame (what the output uses)
+    sdy = (ce * np.sin(az)[None, :]).ravel()
     dz = np.broadcast_to(se, (beams, azimuths)).ravel()
+    px, py, yaw = (0.0, 0.0, 0.0) if pose is None else pose
+    if pose is None:
+        dx, dy = sdx, sdy
+    else:                                             # ray directions in the scene frame
+        dx = (ce * np.cos(az + yaw)[None, :]).ravel()
+        dy = (ce * np.sin(az + yaw)[None, :]).ravel()
     t = np.full(dx.shape, np.inf)
     # ground plane z = -height
     down = dz < -1e-6
@@ -57,7 +67,7 @@ def spinning_lidar_cloud(seed: int, beams: int = 64, azimuths: int = 2083, elev=
     wall_h = rng.uniform(4.0, 12.0, size=2)
     for sign, wi, hi in ((1.0, w[0], wall_h[0]), (-1.0, w[1], wall_h[1])):
         with np.errstate(divide="ignore", invalid="ignore"):
-            tw = (sign * wi) / dy
+            tw = (sign * wi - py) / dy
         z = tw * dz
         ok = (tw > 0) & (z > -height) & (z < hi - height)
         t = np.where(ok & (tw < t), tw, t)
@@ -68,6 +78,7 @@ def spinning_lidar_cloud(seed: int, beams: int = 64, azimuths: int = 2083, elev=
     rad = np.where(rng.random(n_cylinders) < 0.3, rng.uniform(0.8, 1.6, n_cylinders), rng.uniform(0.1, 0.4, n_cylinders))
     top = rng.uniform(1.2, 8.0, size=n_cylinders)
     a2 = dx * dx + dy * dy
+    cx, cy = cx - px, cy - py
     for j in range(n_cylinders):
         b = dx * cx[j] + dy * cy[j]
         cc = cx[j] ** 2 + cy[j] ** 2 - rad[j] ** 2
@@ -78,8 +89,10 @@ def spinning_lidar_cloud(seed: int, beams: int = 64, azimuths: int = 2083, elev=
         ok &= (tc > 0) & (z < top[j] - height) & (z > -height)
         t = np.where(ok & (tc < t), tc, t)
     hit = np.isfinite(t) & (t < max_range) & (t > 0.5)
+    if noise_seed is not None:
+        rng = np.random.default_rng(noise_seed)
     t = t[hit] + rng.normal(0.0, noise, size=int(hit.sum()))
-    pc = np.stack([dx[hit] * t, dy[hit] * t, dz[hit] * t], axis=1)
+    pc = np.stack([sdx[hit] * t, sdy[hit] * t, dz[hit] * t], axis=1)
     return pc.astype(np.float32)
 
 

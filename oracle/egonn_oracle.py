@@ -148,8 +148,8 @@ def forward(sd: Dict[str, torch.Tensor], coords, feats: torch.Tensor, quant: dic
 
     # global head -> decoder -> GeM  (models/minkgl.py:273-286)
     gl = arch["global_levels"]
-    xg = head(sd, "global_head", cm, x, gl, acc64=acc64)
-    xg = _mlp(sd, "global_descriptor_decoder", xg)
+    xg_head = head(sd, "global_head", cm, x, gl, acc64=acc64)
+    xg = _mlp(sd, "global_descriptor_decoder", xg_head)
     cg = cm.coords(1 << min(gl))
     out["global"] = gem(xg, cg, sd["global_pooling.pooling.p"], nb)
 
@@ -185,7 +185,8 @@ def forward(sd: Dict[str, torch.Tensor], coords, feats: torch.Tensor, quant: dic
             oi = torch.from_numpy(me_ops.canonical_order(cm.coords(1 << i)))
             fe[f"down{i}"] = keep[f"down{i}"][oi]
             fe[f"block{i}"] = x[i][oi]
-        fe["global_map"] = xg[torch.from_numpy(me_ops.canonical_order(cg))]
+        fe["global_map"] = xg[torch.from_numpy(me_ops.canonical_order(cg))]            # decoder output (what GeM pools)
+        fe["global_head_map"] = xg_head[torch.from_numpy(me_ops.canonical_order(cg))]  # MinkHead output (engine tap 3)
         fe["local_map"] = xl[ot]
         out["features"] = fe
     return out

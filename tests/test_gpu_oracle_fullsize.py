@@ -75,7 +75,7 @@ def _compare_cloud(model, p, ref, b, errs):
         check(f"down{L}", eng.tap(1, L, fe[f"down{L}"].shape[1])[lo:hi][o], fe[f"down{L}"])
         check(f"block{L}", eng.tap(2, L, fe[f"block{L}"].shape[1])[lo:hi][o], fe[f"block{L}"])
     lo, hi, o = orders[5]
-    check("global_map", eng.tap(3, 5, 128)[lo:hi][o], fe["global_map"])
+    check("global_head_map", eng.tap(3, 5, 128)[lo:hi][o], fe["global_head_map"])
     lo, hi, o = orders[3]
     check("local_map", eng.tap(4, 3, 64)[lo:hi][o], fe["local_map"])
     off3 = p["local_offsets"].cpu().numpy()
