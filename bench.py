@@ -136,7 +136,8 @@ def run_reference(args, rank, world):
         idx = torch.topk(s, k=min(TOPK, s.shape[0]), largest=False).indices
         return out["global"], out["keypoints"][idx], out["descriptors"][idx]
 
-    for _ in range(max(1, min(args.warmup, 1))):
+    warm = max(1, args.warmup)
+    for _ in range(warm):
         step()
     # bounded sample: at most --steps steps and at most ~120 s of host time (one step = one cloud, ~0.9 s on 16 cores)
     steps, t0 = 0, time.perf_counter()
@@ -147,7 +148,7 @@ def run_reference(args, rank, world):
     value = 1.0 / dt
     sample = f"{steps} step(s) of 1 cloud of {args.config} (quantise + forward + top-{TOPK}), torch CPU {cores} threads"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-            "warmup": 1, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": f"synthetic ({wdesc})",
             "config": {"workload": f"{args.config}: {desc}; reference arm runs 1 cloud per step on the host CPU",
                        "note": "ME-semantics CPU restatement (oracle/), not MinkowskiEngine: ME cannot be installed in this image"},

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libegonn_b200.so")
-SOURCES = ["api.cu", "coords.cu", "ops.cu", "forward.cu", "sconv_tc.cu", "sconv_ts.cu", "conv0_tc.cu"]
+SOURCES = ["api.cu", "coords.cu", "ops.cu", "forward.cu", "sconv_tc.cu", "sconv_ts.cu", "conv0_tc.cu", "comm.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
@@ -42,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print("\n".join(log), file=sys.stderr)
     if failed:
         raise RuntimeError("nvcc failed; see egonn_b200/csrc/build.log")
-    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    subprocess.check_call([nvcc, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-ldl"])
     return LIB
 
 

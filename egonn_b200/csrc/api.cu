@@ -77,18 +77,6 @@ int Prof::drain() {
   return EGN_OK;
 }
 
-struct DeviceGuard {
-  int prev = -1;
-  explicit DeviceGuard(int dev) {
-    cudaGetDevice(&prev);
-    if (prev != dev) cudaSetDevice(dev);
-    else prev = -1;
-  }
-  ~DeviceGuard() {
-    if (prev >= 0) cudaSetDevice(prev);
-  }
-};
-
 }  // namespace egn
 
 using namespace egn;
@@ -124,6 +112,11 @@ int egn_ctx_create(egn_ctx **out, int device) {
   ctx->ksplit = ks && ks[0] == '1';
   if (const char *t = getenv("EGN_TRACE")) if (t[0] == '1') { cudaMalloc(&ctx->trace, 64 * 8 * 8); cudaMemset(ctx->trace, 0, 64 * 8 * 8); }
   if (const char *v = getenv("EGN_NSPLIT_MAX")) ctx->nsplit_max = atoi(v);
+  if (const char *v = getenv("EGN_ORDER")) ctx->use_order = v[0] != '0';
+  if (const char *v = getenv("EGN_ORDER_WINDOW")) {
+    const int w = atoi(v);
+    if (w == 2048 || w == 4096 || w == 8192) ctx->order_window = w;
+  }
   if (const char *h = getenv("EGN_HINT_P")) ctx->hint_producer = (unsigned)atoi(h);
   if (const char *h = getenv("EGN_HINT_S")) ctx->hint_single = (unsigned)atoi(h);
   cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);

@@ -35,6 +35,19 @@ void set_error(const char *fmt, ...);
     if (_s != EGN_OK) return _s;                                                                   \
   } while (0)
 
+// make `dev` the current device for the scope (contexts and communicators belong to one device)
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 // ---- key layout --------------------------------------------------------------------------------------
 // level-0 key = (batch << 54) | morton54(ux,uy,uz), u = c + 2^17 in [0, 2^18); x owns the lowest bit of
 // every 3-bit group, so the 3 low bits of a level-L key are exactly MinkowskiEngine's kernel index of

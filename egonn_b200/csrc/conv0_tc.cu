@@ -213,11 +213,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 int run_conv0_tc(egn_ctx *ctx, const void *wpack, const float *scale, const float *shift, int relu, const int *not_ones, int out_split,
                  float *out, double bytes, double flops, cudaStream_t s) {
   const Pyramid &py = ctx->pyr;
-  static bool attr = false;
-  if (!attr) {
-    EGN_CUDA(cudaFuncSetAttribute(c0tc::k_conv0_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, c0tc::kSmemBytes));
-    attr = true;
-  }
+  EGN_SMEM_OPTIN(ctx, c0tc::k_conv0_tc, c0tc::kSmemBytes);
   const int n0 = py.n[0];
   EGN_LAUNCH(ctx, "conv0_5x5x5", bytes, flops, s,
              c0tc::k_conv0_tc<<<(unsigned)div_up(n0, tcx::kRows), c0tc::kThreads, c0tc::kSmemBytes, s>>>(

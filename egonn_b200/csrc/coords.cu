@@ -248,17 +248,19 @@ __global__ void k_batch_offsets(BoffArgs a, int n_batches) {
   a.boff[L][b] = lo;
 }
 
-// 27-neighbour table of the coarsest level by binary search (a few hundred rows per cloud)
-__global__ void k_nbr_top(const uint64_t *__restrict__ keys, int n, int level, int *__restrict__ nbr) {
-  const int64_t total = (int64_t)n * 27;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(t / 27), k = (int)(t % 27);
+// 27-neighbour table of the coarsest level by binary search (a few hundred rows per cloud).  One warp per row: lane k < 27
+// computes entry k, the warp's ballot is the row's 27-bit presence mask (bit k = neighbour k exists).
+__global__ void k_nbr_top(const uint64_t *__restrict__ keys, int n, int level, int *__restrict__ nbr, uint32_t *__restrict__ mask27) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+  const int lim = 1 << (kAxisBits - level);
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
     uint32_t b, vx, vy, vz;
     split_key(level, keys[r], b, vx, vy, vz);
-    const int lim = 1 << (kAxisBits - level);
-    const int nx = (int)vx + (k % 3) - 1, ny = (int)vy + (k / 3) % 3 - 1, nz = (int)vz + k / 9 - 1;
+    const int nx = (int)vx + dx, ny = (int)vy + dy, nz = (int)vz + dz;
     int res = -1;
-    if (nx >= 0 && nx < lim && ny >= 0 && ny < lim && nz >= 0 && nz < lim) {
+    if (lane < 27 && nx >= 0 && nx < lim && ny >= 0 && ny < lim && nz >= 0 && nz < lim) {
       const uint64_t q = make_key(level, b, (uint32_t)nx, (uint32_t)ny, (uint32_t)nz);
       int lo = 0, hi = n;
       while (lo < hi) {
@@ -267,33 +269,173 @@ __global__ void k_nbr_top(const uint64_t *__restrict__ keys, int n, int level, i
       }
       if (lo < n && keys[lo] == q) res = lo;
     }
-    nbr[t] = res;
+    if (lane < 27) nbr[(int64_t)r * 27 + lane] = res;
+    const uint32_t m = __ballot_sync(0xffffffffu, res >= 0);
+    if (lane == 0) mask27[r] = m;
   }
 }
 
 // level L from level L+1: neighbour (c + d) lives in the parent's neighbour (or the parent itself) as the
-// child with code c' ; child row = cstart + popc(mask below c').
+// child with code c' ; child row = cstart + popc(mask below c').  One warp per row (lane = offset k), 108-byte coalesced
+// table rows, presence mask by ballot.
 __global__ void k_nbr_down(const uint64_t *__restrict__ keys, const int *__restrict__ up, int n,
                            const int *__restrict__ nbr_up, const int *__restrict__ cstart_up,
-                           const uint32_t *__restrict__ cmask_up, int *__restrict__ nbr) {
-  const int64_t total = (int64_t)n * 27;
-  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(t / 27), k = (int)(t % 27);
+                           const uint32_t *__restrict__ cmask_up, int *__restrict__ nbr, uint32_t *__restrict__ mask27) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
     const uint32_t code = (uint32_t)(keys[r] & 7ull);
     const int p = up[r];
-    const int px = (int)(code & 1u) + (k % 3) - 1, py = (int)((code >> 1) & 1u) + (k / 3) % 3 - 1,
-              pz = (int)((code >> 2) & 1u) + k / 9 - 1;
-    const int kk = ((px >> 1) + 1) + 3 * ((py >> 1) + 1) + 9 * ((pz >> 1) + 1);
-    const int q = kk == 13 ? p : nbr_up[(int64_t)p * 27 + kk];
     int res = -1;
-    if (q >= 0) {
-      const uint32_t cc = (uint32_t)(px & 1) | ((uint32_t)(py & 1) << 1) | ((uint32_t)(pz & 1) << 2);
-      const uint32_t m = cmask_up[q];
-      if ((m >> cc) & 1u) res = cstart_up[q] + __popc(m & ((1u << cc) - 1u));
+    if (lane < 27) {
+      const int px = (int)(code & 1u) + dx, py = (int)((code >> 1) & 1u) + dy, pz = (int)((code >> 2) & 1u) + dz;
+      const int kk = ((px >> 1) + 1) + 3 * ((py >> 1) + 1) + 9 * ((pz >> 1) + 1);
+      const int q = kk == 13 ? p : nbr_up[(int64_t)p * 27 + kk];
+      if (q >= 0) {
+        const uint32_t cc = (uint32_t)(px & 1) | ((uint32_t)(py & 1) << 1) | ((uint32_t)(pz & 1) << 2);
+        const uint32_t m = cmask_up[q];
+        if ((m >> cc) & 1u) res = cstart_up[q] + __popc(m & ((1u << cc) - 1u));
+      }
+      nbr[(int64_t)r * 27 + lane] = res;
     }
-    nbr[t] = res;
+    const uint32_t m = __ballot_sync(0xffffffffu, res >= 0);
+    if (lane == 0) mask27[r] = m;
   }
 }
+
+// ---- tile row orders ---------------------------------------------------------------------------------------------------
+// The tensor-core convolutions work on tiles of 128 output rows and skip a (tile, 64-element reduction chunk) pair only
+// when NO row of the tile has the chunk's neighbour(s).  In canonical (Morton) order a tile of a LiDAR level fills its
+// chunks to ~30 %: rows on differently oriented surfaces share a tile and the tile pays for the union of their offsets.
+// So every level also gets ROW ORDERS for tiling - permutations of its rows, computed here once per coords_build and
+// shared by all convolutions of the level - in which rows with similar offset sets are adjacent:
+//   kind 0 (3x3x3):            rows sorted by their 27-bit presence mask with the bits ranked rare -> significant
+//                              (corner offsets, then edges, then faces; vertical before horizontal) so that the rows
+//                              owning a rare offset are isolated in few tiles;
+//   kind 1 (2x2x2 stride 2):   output (parent) rows sorted by their 8-bit child mask;
+//   kind 2 (transposed 2x2x2): output (fine) rows sorted by their own child code (each row uses exactly one kernel slice).
+// Rows are only re-grouped inside windows of W (4096 by default) canonical rows - one CTA sorts one window in shared
+// memory (stable radix sort, deterministic) - so a tile still gathers from a compact neighbourhood.  The maps themselves stay in canonical order: only the tile -> row assignment changes.
+constexpr int kOrderThreads = 1024;
+constexpr int kMaxOrderJobs = 3 * P;
+
+struct OrderJob {
+  const void *src;      // kind 0: uint32 mask27[n]; kind 1: uint32 cmask[n]; kind 2: uint64 keys[n]
+  int *out;             // order[n]
+  int n, kind, first_block;
+};
+struct OrderJobs {
+  OrderJob job[kMaxOrderJobs];
+  int n_jobs;
+};
+
+// sort-key position of offset k (13 = centre: always present, not part of the key); most common offsets -> low bits
+__constant__ int8_t c_order_bitpos[27] = {18, 10, 19, 11, 4, 12, 20, 13, 21, 6, 0, 7, 1, -1, 2, 8, 3, 9, 22, 14, 23, 15, 5, 16, 24, 17, 25};
+
+// One CTA sorts one window of W rows by (key, row) in shared memory: LSD radix sort with 8-bit digits (4 passes for the
+// 26-bit 3x3x3 keys, 1 pass for the 8-bit child masks and 3-bit child codes).  A warp owns W/32 consecutive elements and
+// ranks them in order with __match_any_sync (stable), per-(digit, warp) counters are scanned digit-major by the block.
+template <int W>
+__global__ void __launch_bounds__(kOrderThreads) k_order_windows(OrderJobs jobs) {
+  constexpr int ROUNDS = W / kOrderThreads;
+  extern __shared__ __align__(16) uint8_t order_smem[];
+  uint32_t *key_a = (uint32_t *)order_smem, *key_b = key_a + W;
+  uint16_t *idx_a = (uint16_t *)(key_b + W), *idx_b = idx_a + W;
+  uint16_t *cnt = idx_b + W;                                   // [256 digits][32 warps]
+  __shared__ int warp_sums[32];
+  int j = 0;
+  while (j + 1 < jobs.n_jobs && (int)blockIdx.x >= jobs.job[j + 1].first_block) ++j;
+  const OrderJob &jb = jobs.job[j];
+  const int base = ((int)blockIdx.x - jb.first_block) * W;
+  const int count = min(W, jb.n - base);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < W; i += kOrderThreads) {
+    uint32_t k32 = 0xffffffffu;
+    if (i < count) {
+      if (jb.kind == 0) {
+        const uint32_t m = ((const uint32_t *)jb.src)[base + i];
+        k32 = 0;
+#pragma unroll
+        for (int k = 0; k < 27; ++k)
+          if (k != 13) k32 |= ((m >> k) & 1u) << c_order_bitpos[k];
+      } else if (jb.kind == 1) {
+        k32 = ((const uint32_t *)jb.src)[base + i] & 0xffu;
+      } else {
+        k32 = (uint32_t)(((const uint64_t *)jb.src)[base + i] & 7ull);
+      }
+    }
+    key_a[i] = k32;
+    idx_a[i] = (uint16_t)i;
+  }
+  const int passes = jb.kind == 0 ? 4 : 1;
+  for (int p = 0; p < passes; ++p) {
+    for (int i = tid; i < 256 * 32; i += kOrderThreads) cnt[i] = 0;
+    __syncthreads();
+    // rank inside the warp's segment (elements warp*W/32 + round*32 + lane, visited in order)
+    uint32_t key[ROUNDS];
+    uint16_t idx[ROUNDS], rank[ROUNDS];
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const int e = warp * (W / 32) + r * 32 + lane;
+      key[r] = key_a[e];
+      idx[r] = idx_a[e];
+      const uint32_t d = (key[r] >> (8 * p)) & 255u;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      const int leader = __ffs(peers) - 1;
+      uint16_t old = 0;
+      if (lane == leader) {
+        old = cnt[d * 32 + warp];
+        cnt[d * 32 + warp] = (uint16_t)(old + __popc(peers));
+      }
+      old = (uint16_t)__shfl_sync(0xffffffffu, (int)old, leader);
+      rank[r] = (uint16_t)(old + __popc(peers & ((1u << lane) - 1u)));
+      __syncwarp();
+    }
+    __syncthreads();
+    // exclusive scan of the 8192 counters in (digit, warp) order: 8 per thread
+    {
+      int v[8], sum = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { v[e] = cnt[tid * 8 + e]; sum += v[e]; }
+      int incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      if (lane == 31) warp_sums[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        int w = warp_sums[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, wi, o);
+          if (lane >= o) wi += t;
+        }
+        warp_sums[lane] = wi - w;
+      }
+      __syncthreads();
+      int run = warp_sums[warp] + incl - sum;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { cnt[tid * 8 + e] = (uint16_t)run; run += v[e]; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+      const uint32_t d = (key[r] >> (8 * p)) & 255u;
+      const int pos = cnt[d * 32 + warp] + rank[r];
+      key_b[pos] = key[r];
+      idx_b[pos] = idx[r];
+    }
+    __syncthreads();
+    uint32_t *tk = key_a; key_a = key_b; key_b = tk;
+    uint16_t *ti = idx_a; idx_a = idx_b; idx_b = ti;
+  }
+  for (int i = tid; i < count; i += kOrderThreads) jb.out[base + i] = base + (int)idx_a[i];
+}
+
+static size_t order_smem_bytes(int w) { return (size_t)w * 12 + 256 * 32 * 2; }
 
 __global__ void k_decode_coords(const uint64_t *__restrict__ keys, int n, int level, int4 *__restrict__ out) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -450,7 +592,7 @@ static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64
   size_t need = 0;
   for (int L = 0; L < P; ++L) {
     const size_t m = (size_t)hc.totals[L];
-    need += pad256(m * 8) + 3 * pad256(m * 4) + pad256(m * 27 * 4) + pad256((size_t)(B + 1) * 4);
+    need += pad256(m * 8) + 7 * pad256(m * 4) + pad256(m * 27 * 4) + pad256((size_t)(B + 1) * 4);
   }
   need += pad256((size_t)hc.totals[0] * 4) + pad256((size_t)hc.totals[2] * 8) + pad256((size_t)hc.totals[2] * 4) + 4096;
   Arena &ca = ctx->coords;
@@ -464,8 +606,13 @@ static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64
     py.cstart[L] = lp.cstart[L] = (int *)ca.take(m * 4);
     py.cmask[L] = lp.cmask[L] = (uint32_t *)ca.take(m * 4);
     py.nbr[L] = L >= 1 ? (int *)ca.take(m * 27 * 4) : nullptr;
+    py.mask27[L] = L >= 1 ? (uint32_t *)ca.take(m * 4) : nullptr;
+    py.ord27[L] = L >= 1 ? (int *)ca.take(m * 4) : nullptr;
+    py.ordc[L] = L >= 1 ? (int *)ca.take(m * 4) : nullptr;
+    py.ordt[L] = L + 1 < P ? (int *)ca.take(m * 4) : nullptr;
     py.boff[L] = (int *)ca.take((size_t)(B + 1) * 4);
-    EGN_CHECK(py.keys[L] && py.up[L] && py.cstart[L] && py.cmask[L] && py.boff[L] && (L == 0 || py.nbr[L]),
+    EGN_CHECK(py.keys[L] && py.up[L] && py.cstart[L] && py.cmask[L] && py.boff[L] && (L == 0 || (py.nbr[L] && py.mask27[L] && py.ord27[L] && py.ordc[L])) &&
+                  (L + 1 >= P || py.ordt[L]),
               EGN_ERR_STATE, "coords arena exhausted");
     if (L >= 1) EGN_CUDA(cudaMemsetAsync(py.cmask[L], 0, m * 4, s));
   }
@@ -494,12 +641,41 @@ static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64
   // kernel-map build: algorithmic bytes N*8 (keys) + N*27*4 (table) per level
   const int T = P - 1;
   EGN_LAUNCH(ctx, "kernel_map_3x3x3", (double)py.n[T] * (8 + 108), 0, s,
-             k_nbr_top<<<grid_for((int64_t)py.n[T] * 27, 256), 256, 0, s>>>(py.keys[T], py.n[T], T, py.nbr[T]));
+             k_nbr_top<<<grid_for((int64_t)py.n[T] * 32, 256), 256, 0, s>>>(py.keys[T], py.n[T], T, py.nbr[T], py.mask27[T]));
   for (int L = T - 1; L >= 1; --L)
     EGN_LAUNCH(ctx, "kernel_map_3x3x3", (double)py.n[L] * (8 + 108), 0, s,
-               k_nbr_down<<<grid_for((int64_t)py.n[L] * 27, 256), 256, 0, s>>>(py.keys[L], py.up[L], py.n[L], py.nbr[L + 1],
-                                                                                 py.cstart[L + 1], py.cmask[L + 1], py.nbr[L]));
+               k_nbr_down<<<grid_for((int64_t)py.n[L] * 32, 256), 256, 0, s>>>(py.keys[L], py.up[L], py.n[L], py.nbr[L + 1],
+                                                                                 py.cstart[L + 1], py.cmask[L + 1], py.nbr[L], py.mask27[L]));
   EGN_CUDA(cudaGetLastError());
+  if (ctx->use_order) {   // tile row orders of every level: ONE launch, one CTA per window of kOrderWindow rows
+    const int kOrderWindow = (ctx->order_window == 2048 || ctx->order_window == 8192) ? ctx->order_window : 4096;
+    OrderJobs oj;
+    oj.n_jobs = 0;
+    int blocks = 0;
+    double rows = 0;
+    auto add = [&](const void *src, int *out, int n_rows, int kind) {
+      if (n_rows <= 0) return;
+      OrderJob &jb = oj.job[oj.n_jobs++];
+      jb.src = src; jb.out = out; jb.n = n_rows; jb.kind = kind; jb.first_block = blocks;
+      blocks += (int)div_up(n_rows, kOrderWindow);
+      rows += n_rows;
+    };
+    for (int L = 1; L < P; ++L) add(py.mask27[L], py.ord27[L], py.n[L], 0);
+    for (int L = 1; L < P; ++L) add(py.cmask[L], py.ordc[L], py.n[L], 1);
+    for (int L = 0; L + 1 < P; ++L) add(py.keys[L], py.ordt[L], py.n[L], 2);
+    if (kOrderWindow == 2048) {
+      EGN_SMEM_OPTIN(ctx, k_order_windows<2048>, order_smem_bytes(2048));
+      EGN_LAUNCH(ctx, "tile_row_orders", rows * 8, 0, s, k_order_windows<2048><<<blocks, kOrderThreads, order_smem_bytes(2048), s>>>(oj));
+    } else if (kOrderWindow == 8192) {
+      EGN_SMEM_OPTIN(ctx, k_order_windows<8192>, order_smem_bytes(8192));
+      EGN_LAUNCH(ctx, "tile_row_orders", rows * 8, 0, s, k_order_windows<8192><<<blocks, kOrderThreads, order_smem_bytes(8192), s>>>(oj));
+    } else {
+      EGN_SMEM_OPTIN(ctx, k_order_windows<4096>, order_smem_bytes(4096));
+      EGN_LAUNCH(ctx, "tile_row_orders", rows * 8, 0, s, k_order_windows<4096><<<blocks, kOrderThreads, order_smem_bytes(4096), s>>>(oj));
+    }
+    EGN_CUDA(cudaGetLastError());
+    py.ordered = true;
+  }
   py.n_input = n;
   py.n_batches = B;
   py.valid = true;

@@ -1,5 +1,6 @@
 // Engine context: coordinate pyramid ("coordinate manager") + scratch arenas.
 #pragma once
+#include <unordered_set>
 #include <vector>
 
 #include "common.cuh"
@@ -18,6 +19,13 @@ struct Pyramid {
   int *cstart[P] = {nullptr};      // row at L -> first child row at L-1      (L >= 1)
   uint32_t *cmask[P] = {nullptr};  // row at L -> 8-bit child occupancy       (L >= 1)
   int *nbr[P] = {nullptr};         // (n[L],27) neighbour rows at L, -1 absent (L >= 1)
+  uint32_t *mask27[P] = {nullptr}; // row at L -> 27-bit presence mask of its 3x3x3 neighbourhood (L >= 1)
+  // tile row orders (coords.cu "tile row orders"): permutations of the level's rows used ONLY to form the 128-row tiles of
+  // the tensor-core convolutions - rows with similar offset sets adjacent, so that whole (tile, chunk) pairs vanish
+  int *ord27[P] = {nullptr};       // 3x3x3 convolutions at L            (L >= 1)
+  int *ordc[P] = {nullptr};        // 2x2x2 stride-2 convolution INTO L  (L >= 1; keyed by the child mask)
+  int *ordt[P] = {nullptr};        // transposed 2x2x2 convolution INTO L (L < P-1; keyed by the row's own child code)
+  bool ordered = false;
   int *boff[P] = {nullptr};        // (n_batches+1) first row of each batch
   int *perm0 = nullptr;            // canonical L0 row -> input row
   uint64_t *mask64 = nullptr;      // per L2 cell: occupancy of its 4x4x4 level-0 voxels (bit = key0 & 63)
@@ -73,6 +81,11 @@ struct egn_ctx {
   egn::Taps taps;
   egn::Prof prof;
   bool use_tc = true;
+  bool use_order = true;            // mask-sorted tile row orders for the tensor-core convolutions (EGN_ORDER=0 disables)
+  int order_window = 4096;          // rows are re-grouped inside windows of this many canonical rows (EGN_ORDER_WINDOW = 2048 | 4096 | 8192)
+  // kernels already opted in to > 48 KB dynamic shared memory ON THIS CONTEXT'S DEVICE: the attribute is per device, a
+  // context belongs to one device, so the bookkeeping lives here and not in process-wide statics (egn_smem_optin below)
+  std::unordered_set<const void *> smem_optin;
   cudaStream_t aux = nullptr;       // second stream: the local head overlaps the upper trunk levels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   const void *win_ptr = nullptr;    // persisting-L2 window over the weight blob (egn_weights_resident)
@@ -84,6 +97,16 @@ struct egn_ctx {
   void *splitk_buf = nullptr;       // raw partial tiles of K-split convolutions (small levels only)
   size_t splitk_cap = 0;
 };
+
+// opt a kernel in to `bytes` of dynamic shared memory once per context (the current device must be ctx->device)
+#define EGN_SMEM_OPTIN(ctx, kernel, bytes)                                                                              \
+  do {                                                                                                                   \
+    const void *egn_f_ = (const void *)(kernel);                                                                         \
+    if (!(ctx)->smem_optin.count(egn_f_)) {                                                                              \
+      EGN_CUDA(cudaFuncSetAttribute(egn_f_, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));                 \
+      (ctx)->smem_optin.insert(egn_f_);                                                                                  \
+    }                                                                                                                    \
+  } while (0)
 
 // bracket one kernel class: counts the launch, and in profile mode records start/stop events
 #define EGN_LAUNCH(ctx, name, bytes, flops, stream, ...)            \

@@ -646,12 +646,8 @@ int run_conv0(egn_ctx *ctx, int ksize, const float *f0, const float *w, const fl
   const int blocks0 = (int)std::min<int64_t>(div_up(n0, C0<false>::kWarps * 32), (int64_t)kNumSMs * C0<false>::kCtas * 4);
 #define EGN_C0(KS, NAME)                                                                                                    \
   {                                                                                                                         \
-    static bool attr = false;                                                                                               \
-    if (!attr) {                                                                                                            \
-      EGN_CUDA(cudaFuncSetAttribute(k_conv0<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));           \
-      EGN_CUDA(cudaFuncSetAttribute(k_conv0<KS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0));          \
-      attr = true;                                                                                                          \
-    }                                                                                                                       \
+    EGN_SMEM_OPTIN(ctx, (k_conv0<KS, true>), smem1);                                                                        \
+    EGN_SMEM_OPTIN(ctx, (k_conv0<KS, false>), smem0);                                                                       \
     if (not_ones && wtc && KS == 5)                                                                                         \
       EGN_TRY(run_conv0_tc(ctx, wtc, scale, shift, relu, not_ones, out_split, out, bytes, flops, s));                       \
     else if (not_ones)                                                                                                      \

@@ -67,16 +67,19 @@ int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, 
   } else if (ksize == 3) {
     EGN_CHECK(level_in >= 1 && level_in < P, EGN_ERR_INVALID, "conv k=3: bad level");
     a.mode = 1; a.n_out = py.n[level_in]; a.nbr = py.nbr[level_in]; a.zero_row = py.n[level_in];
+    if (py.ordered) a.order = py.ord27[level_in];
     pairs = py.pairs27[level_in];
     snprintf(name, sizeof(name), "tc_conv3x3x3_c%d_%d", cin, cout);
   } else if (transposed) {
     EGN_CHECK(level_in >= 1 && level_in < P, EGN_ERR_INVALID, "transposed conv: bad level");
     a.mode = 3; a.n_out = py.n[level_in - 1]; a.up = py.up[level_in - 1]; a.keys = py.keys[level_in - 1]; a.zero_row = py.n[level_in];
+    if (py.ordered) a.order = py.ordt[level_in - 1];
     pairs = a.n_out;
     snprintf(name, sizeof(name), "tc_tconv2x2x2s2_c%d_%d", cin, cout);
   } else {
     EGN_CHECK(level_in >= 0 && level_in + 1 < P, EGN_ERR_INVALID, "conv k=2: bad level");
     a.mode = 2; a.n_out = py.n[level_in + 1]; a.cstart = py.cstart[level_in + 1]; a.cmask = py.cmask[level_in + 1]; a.zero_row = py.n[level_in];
+    if (py.ordered) a.order = py.ordc[level_in + 1];
     pairs = py.n[level_in];
     snprintf(name, sizeof(name), "tc_conv2x2x2s2_c%d_%d", cin, cout);
   }

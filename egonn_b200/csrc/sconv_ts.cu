@@ -41,15 +41,19 @@ struct Cfg {
   static constexpr int kAccCols = kBig ? 128 : 64;         // A stages start here; accumulator = columns [0, COUT)
   static constexpr int kThreads = (kProducerWarps + 2) * 32;
   static constexpr int kBBytes = 2 * COUT * 128;           // hi + lo image of one weight chunk
-  static constexpr int kSmemBytes = kStages * kBBytes + kRows * 27 * 4 + 1024;
+  static constexpr int kSmemBytes = kStages * kBBytes + kRows * 27 * 4 + 1536;
 };
 
 // SPLIT_IN: the input feature map is in the engine's pre-split format (common.cuh: every 4 channels = 16 bytes
 // [hi0 hi1 hi2 hi3 | lo0 lo1 lo2 lo3] bf16 - what the producing kernel's epilogue wrote) AND has an all-zero row at
 // index a.zero_row that absent neighbours point to: the gather is then 16-byte loads straight into the tcgen05.st
 // registers - no conversion, no predication.  Otherwise: fp32 rows, predicated loads, bf16 hi/lo split in registers.
-template <int CIN, int COUT, int KOFF, bool SPLIT_IN>
+// MODE (compile time - a run-time switch in the prologue made the compiler emit a jump table per table entry and the
+// dependent loads of consecutive entries serialised: 5-10 k cycles per tile): 0 identity rows (1x1x1), 1 27-neighbour
+// table, 2 2x2x2 stride-2 children, 3 transposed 2x2x2 (parent row, kernel slice = the row's own child code).
+template <int CIN, int COUT, int KOFF, bool SPLIT_IN, int MODE>
 __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCtasPerSm) k_sconv_ts(Args a) {
+  static_assert((MODE == 0 && KOFF == 1) || (MODE == 1 && KOFF == 27) || ((MODE == 2 || MODE == 3) && KOFF == 8), "mode / offsets");
   using C = Cfg<CIN, COUT>;
   constexpr int kStages = C::kStages, NG = C::kGroups;
   constexpr int NPW = C::kProducerWarps, NT = C::kThreads;
@@ -65,6 +69,7 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   int *s_nlist = (int *)(s_tmem + 1);
   uint32_t *s_present = (uint32_t *)(s_nlist + 1);                // [2] bit j: chunk j has at least one present row
   int *s_list = (int *)(s_present + 2);                           // [NCH] compacted chunk ids
+  int *s_rows = s_list + 56;                                      // [kRows] output row of every tile slot (tile row order, ctx.cuh)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * kRows;
@@ -73,22 +78,71 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   const bool trc = a.trace != nullptr && blockIdx.x == (gridDim.x >> 1) && blockIdx.y == 0 && blockIdx.z == 0;
   if (trc && tid == 0) a.trace[60 * 8 + 0] = clock64();
 
-  // neighbour rows of the tile: the global loads go out FIRST, their latency overlaps barrier setup and TMEM allocation
+  // neighbour rows of the tile: the global loads go out FIRST (their latency overlaps barrier setup and TMEM allocation),
+  // in two branch-free batches - every thread first fetches the output rows of its table entries (tile slot -> row through
+  // the level's tile row order), then the entries themselves: two memory latencies per tile, whatever the entry count.
   int src[NBR_ITERS];
+  {
+    int rowv[NBR_ITERS];
 #pragma unroll
-  for (int it = 0; it < NBR_ITERS; ++it) {
-    const int t = tid + it * NT;
-    const int r = t / KOFF, k = t - r * KOFF, row = row0 + r;
-    src[it] = -1;
-    if (t < kRows * KOFF && row < a.n_out) {
-      if (a.mode == 0) src[it] = row;
-      else if (a.mode == 1) src[it] = __ldg(a.nbr + (int64_t)row0 * 27 + t);
-      else if (a.mode == 2) {
-        const uint32_t m = __ldg(a.cmask + row);
-        if ((m >> k) & 1u) src[it] = __ldg(a.cstart + row) + __popc(m & ((1u << k) - 1u));
-      } else {
-        if ((int)(__ldg(a.keys + row) & 7ull) == k) src[it] = __ldg(a.up + row);
+    for (int it = 0; it < NBR_ITERS; ++it) {
+      const int t = tid + it * NT;
+      const int r = t / KOFF;
+      const bool ok = t < kRows * KOFF && row0 + r < a.n_out;
+      rowv[it] = ok ? row0 + r : -1;
+    }
+    if (a.order != nullptr) {
+#pragma unroll
+      for (int it = 0; it < NBR_ITERS; ++it) {
+        const int v = __ldg(a.order + (rowv[it] >= 0 ? rowv[it] : 0));
+        rowv[it] = rowv[it] >= 0 ? v : -1;
       }
+    }
+    if constexpr (MODE == 0) {
+#pragma unroll
+      for (int it = 0; it < NBR_ITERS; ++it) src[it] = rowv[it];
+    } else if constexpr (MODE == 1) {
+#pragma unroll
+      for (int it = 0; it < NBR_ITERS; ++it) {
+        const int t = tid + it * NT;
+        const int k = t - (t / KOFF) * KOFF;
+        const int v = __ldg(a.nbr + (int64_t)(rowv[it] >= 0 ? rowv[it] : 0) * 27 + k);
+        src[it] = rowv[it] >= 0 ? v : -1;
+      }
+    } else if constexpr (MODE == 2) {
+      uint32_t m[NBR_ITERS];
+      int cs[NBR_ITERS];
+#pragma unroll
+      for (int it = 0; it < NBR_ITERS; ++it) {
+        const int rr = rowv[it] >= 0 ? rowv[it] : 0;
+        m[it] = __ldg(a.cmask + rr);
+        cs[it] = __ldg(a.cstart + rr);
+      }
+#pragma unroll
+      for (int it = 0; it < NBR_ITERS; ++it) {
+        const int k = (tid + it * NT) & 7;
+        src[it] = (rowv[it] >= 0 && ((m[it] >> k) & 1u)) ? cs[it] + __popc(m[it] & ((1u << k) - 1u)) : -1;
+      }
+    } else {
+      uint32_t code[NBR_ITERS];
+      int par[NBR_ITERS];
+#pragma unroll
+      for (int it = 0; it < NBR_ITERS; ++it) {
+        const int rr = rowv[it] >= 0 ? rowv[it] : 0;
+        code[it] = (uint32_t)(__ldg(a.keys + rr) & 7ull);
+        par[it] = __ldg(a.up + rr);
+      }
+#pragma unroll
+      for (int it = 0; it < NBR_ITERS; ++it) {
+        const int k = (tid + it * NT) & 7;
+        src[it] = (rowv[it] >= 0 && (int)code[it] == k) ? par[it] : -1;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < NBR_ITERS; ++it) {
+      const int t = tid + it * NT;
+      const int r = t / KOFF;
+      if (t < kRows * KOFF && t - r * KOFF == 0) s_rows[r] = rowv[it];     // -1 beyond the last row of the map
     }
   }
   if (tid == 0) {
@@ -242,57 +296,74 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
       if (tr) a.trace[i * 8 + 7] = clock64();
     }
     if (trc && warp == 0 && lane == 0) a.trace[60 * 8 + 2] = clock64();
-    // ===================== epilogue: TMEM -> scale/shift/relu -> global =====================
+    // ===================== epilogue: TMEM -> shared memory (the idle weight ring) -> scale/shift/relu -> global ==============
+    // A thread owns one accumulator ROW (TMEM lane), so storing straight from the tcgen05.ld registers touches 32
+    // different output rows per instruction (one 16-byte sector each).  The tile is transposed through shared memory
+    // instead - the weight ring is idle once the accumulator barrier has fired - and leaves as whole rows: a warp
+    // instruction writes 512 contiguous bytes of 1, 2 or 4 output rows.  Row r's 16-byte unit u sits at unit u ^ (r & 7):
+    // conflict-free both ways.
     constexpr int CPW = COUT / NG;                                           // accumulator columns per warp (>= 16)
     static_assert(CPW >= 16 && CPW % 16 == 0, "tcgen05.ld granularity: 16 columns");
+    static_assert(kStages * C::kBBytes >= kRows * COUT * 4, "the weight ring must hold one fp32 output tile");
     if (nlist > 0) {
       mbar_wait(accum, 0u, a.hint_producer);
       tc_fence_after();
     }
     if (trc && warp == 0 && lane == 0) a.trace[60 * 8 + 3] = clock64();
-    const int row = row0 + q * 32 + lane;
-    float *obase = a.out + (size_t)blockIdx.z * a.n_out * a.cout_total;
+    constexpr int UPR = COUT / 4;                                            // 16-byte units per output row
+    float4 *stage = (float4 *)btiles;
+    {
+      const int r = q * 32 + lane;
 #pragma unroll
-    for (int cc = 0; cc < CPW; cc += 16) {
-      const int c0 = g * CPW + cc;
-      uint32_t r[16];
-      if (nlist > 0) {
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-        if constexpr (C::kFold) {                            // + the hi*lo half of the folded accumulator
-          uint32_t r2[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(COUT + c0), r2);
+      for (int cc = 0; cc < CPW; cc += 16) {
+        const int c0 = g * CPW + cc;
+        uint32_t v[16];
+        if (nlist > 0) {
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+          if constexpr (C::kFold) {                            // + the hi*lo half of the folded accumulator
+            uint32_t v2[16];
+            tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(COUT + c0), v2);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + __uint_as_float(r2[e]));
+            for (int e = 0; e < 16; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(v2[e]));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] = 0u;             // no chunk of this split touches the tile: partial = 0
         }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 16; ++e) r[e] = 0u;             // no chunk of this split touches the tile: partial = 0
-      }
-      if (row < a.n_out) {
-        float *o = obase + (size_t)row * a.cout_total + col0 + c0;
 #pragma unroll
         for (int gg = 0; gg < 4; ++gg) {
-          float4 y;
-          float *yy = (float *)&y;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = col0 + c0 + gg * 4 + e;
-            float val = __uint_as_float(r[gg * 4 + e]);
-            if (a.scale) val *= __ldg(a.scale + c);
-            if (a.shift) val += __ldg(a.shift + c);
-            if (a.relu) val = fmaxf(val, 0.f);
-            yy[e] = val;
-          }
-          if (a.accumulate) {
-            const float4 prev = *(const float4 *)(o + gg * 4);
-            y.x += prev.x; y.y += prev.y; y.z += prev.z; y.w += prev.w;
-          }
-          if (a.out_split) {                               // pre-split output: [hi0..3 | lo0..3] bf16 in the same 16 bytes
-            *(uint4 *)(o + gg * 4) = presplit_pack(y);
-          } else {
-            *(float4 *)(o + gg * 4) = y;
-          }
+          const int u = (c0 >> 2) + gg;
+          stage[r * UPR + (u ^ (r & 7))] = make_float4(__uint_as_float(v[gg * 4]), __uint_as_float(v[gg * 4 + 1]), __uint_as_float(v[gg * 4 + 2]),
+                                                       __uint_as_float(v[gg * 4 + 3]));
         }
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NPW * 32) : "memory");              // producer warps only: the tile is staged
+    {
+      constexpr int RPI = 32 / UPR > 0 ? 32 / UPR : 1;                       // rows per warp instruction (4, 2 or 1)
+      constexpr int UPL = UPR / 32 > 0 ? UPR / 32 : 1;                       // units per lane per row (1)
+      static_assert(UPL == 1, "at most 128 output channels per CTA");
+      const int u = lane % UPR, rsub = lane / UPR;
+      const int c = col0 + 4 * u;
+      float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (a.scale) sc = __ldg((const float4 *)(a.scale + c));
+      if (a.shift) sh = __ldg((const float4 *)(a.shift + c));
+      float *obase = a.out + (size_t)blockIdx.z * a.n_out * a.cout_total;
+#pragma unroll 4
+      for (int rb = warp * RPI; rb < kRows; rb += NPW * RPI) {
+        const int r = rb + rsub;
+        const int row = s_rows[r];
+        if (row < 0) continue;
+        float4 y = stage[r * UPR + (u ^ (r & 7))];
+        y.x = y.x * sc.x + sh.x; y.y = y.y * sc.y + sh.y; y.z = y.z * sc.z + sh.z; y.w = y.w * sc.w + sh.w;
+        if (a.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+        float *o = obase + (size_t)row * a.cout_total + c;
+        if (a.accumulate) {
+          const float4 prev = *(const float4 *)o;
+          y.x += prev.x; y.y += prev.y; y.z += prev.z; y.w += prev.w;
+        }
+        if (a.out_split) *(uint4 *)o = presplit_pack(y);       // pre-split output: [hi0..3 | lo0..3] bf16 in the same 16 bytes
+        else *(float4 *)o = y;
       }
     }
     // the all-zero row behind the last output row (what absent neighbours of the NEXT convolution point to)
@@ -361,23 +432,20 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   }
 }
 
-template <int CIN, int COUT, int KOFF, bool SPLIT_IN>
+template <int CIN, int COUT, int KOFF, bool SPLIT_IN, int MODE>
 static int launch1(egn_ctx *ctx, const Args &a, const char *name, double bytes, double flops, cudaStream_t s) {
   using C = Cfg<CIN, COUT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EGN_CUDA(cudaFuncSetAttribute(k_sconv_ts<CIN, COUT, KOFF, SPLIT_IN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_done = true;
-  }
+  EGN_SMEM_OPTIN(ctx, (k_sconv_ts<CIN, COUT, KOFF, SPLIT_IN, MODE>), C::kSmemBytes);
   const dim3 grid((unsigned)div_up(a.n_out, kRows), (unsigned)(a.cout_total / COUT), (unsigned)a.ksplit);
-  EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv_ts<CIN, COUT, KOFF, SPLIT_IN><<<grid, C::kThreads, C::kSmemBytes, s>>>(a));
+  EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv_ts<CIN, COUT, KOFF, SPLIT_IN, MODE><<<grid, C::kThreads, C::kSmemBytes, s>>>(a));
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
 }
 
-template <int CIN, int COUT, int KOFF>
+template <int CIN, int COUT, int KOFF, int MODE>
 static int launch(egn_ctx *ctx, const Args &a, const char *name, double bytes, double flops, cudaStream_t s) {
-  return a.in_split ? launch1<CIN, COUT, KOFF, true>(ctx, a, name, bytes, flops, s) : launch1<CIN, COUT, KOFF, false>(ctx, a, name, bytes, flops, s);
+  return a.in_split ? launch1<CIN, COUT, KOFF, true, MODE>(ctx, a, name, bytes, flops, s)
+                    : launch1<CIN, COUT, KOFF, false, MODE>(ctx, a, name, bytes, flops, s);
 }
 
 }  // namespace ts
@@ -385,8 +453,11 @@ static int launch(egn_ctx *ctx, const Args &a, const char *name, double bytes, d
 // dispatch of one (CIN, COUT-per-CTA, KOFF) instance; returns EGN_ERR_INVALID when there is no such instance
 int launch_conv_ts(egn_ctx *ctx, int koff, int cin, int cout_cta, const tcx::Args &a, const char *name, double bytes, double flops,
                    cudaStream_t s) {
-#define EGN_TS_CASE(KO, CI, CO) \
-  if (koff == KO && cin == CI && cout_cta == CO) return ts::launch<CI, CO, KO>(ctx, a, name, bytes, flops, s);
+#define EGN_TS_CASE(KO, CI, CO)                                                                                         \
+  if (koff == KO && cin == CI && cout_cta == CO) {                                                                      \
+    if (KO == 8 && a.mode == 3) return ts::launch<CI, CO, KO, KO == 8 ? 3 : (KO == 27 ? 1 : 0)>(ctx, a, name, bytes, flops, s); \
+    return ts::launch<CI, CO, KO, KO == 27 ? 1 : (KO == 8 ? 2 : 0)>(ctx, a, name, bytes, flops, s);                     \
+  }
   EGN_TS_CASE(27, 32, 32)
   EGN_TS_CASE(27, 32, 64)
   EGN_TS_CASE(27, 64, 64)

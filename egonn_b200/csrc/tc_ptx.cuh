@@ -205,7 +205,7 @@ __device__ __forceinline__ void ldg256_pred(const float *p, bool pred, float4 &a
 // A feature map that only tensor-core convolutions gather from is stored PRE-SPLIT: same (n, C) x 4-byte footprint as
 // fp32, but every group of 4 channels is the 16 bytes [hi0 hi1 hi2 hi3 | lo0 lo1 lo2 lo3] (bf16; x = hi + lo to 2^-17
 // relative - exactly the rounding the tensor-core path applies to its A operand anyway).  The producing kernel's
-// epilogue splits each value ONCE; the ~8.5 gathers per value of a 3x3x3 convolution then move bits only.  Such a map
+// epilogue splits each value ONCE; the ~7 gathers per value of a 3x3x3 convolution then move bits only.  Such a map
 // also carries one all-zero row at index n, which absent neighbours point to (no predication in the gather).
 __device__ __forceinline__ uint4 presplit_pack(float4 y) {
   uint4 u;
@@ -231,6 +231,7 @@ struct Args {
   long long *trace;                      // debug: clock64 timeline of CTA 0 (null in production)
   uint32_t hint_producer, hint_single;   // try_wait suspend hints (ns) for the gather warps / the TMA and MMA threads
   int n_out, relu, accumulate, cout_total, ksplit, mode;   // ksplit > 1: grid.z partitions the chunks, raw partials to out + z*n_out*cout_total  // mode 0: identity rows (1x1x1 convolution), 1: 27-neighbour table, 2: 2x2x2 stride-2 children, 3: transposed 2x2x2 (parent, slice = own code)
+  const int *order;        // tile slot -> output row (null: identity); coords.cu "tile row orders"
   const int *nbr;
   const int *cstart;
   const uint32_t *cmask;

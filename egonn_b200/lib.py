@@ -77,6 +77,10 @@ _SIGNATURES = {
     "egn_launch_count": (C.c_int64, [_P]),
     "egn_debug_trace": (C.c_int, [_P, _P]),
     "egn_topk_smallest": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "egn_comm_unique_id": (C.c_int, [_P]),
+    "egn_comm_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, _P]),
+    "egn_comm_destroy": (C.c_int, [_P]),
+    "egn_allgather_global": (C.c_int, [_P, _P, _P, C.c_int64, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 
@@ -90,6 +94,14 @@ def load() -> C.CDLL:
         if not os.path.exists(LIB_PATH):
             raise EgnError(f"{LIB_PATH} is missing: run `python -m egonn_b200.build` (nvcc, sm_100a). "
                            "egonn_b200 has no CPU / PyTorch fallback.")
+        if "EGN_NCCL_LIB" not in os.environ:       # egn_comm_* dlopen NCCL at first use: point them at PyTorch's bundled copy
+            try:
+                import nvidia.nccl as _nccl
+                cand = os.path.join(list(_nccl.__path__)[0], "lib", "libnccl.so.2")
+                if os.path.exists(cand):
+                    os.environ["EGN_NCCL_LIB"] = cand
+            except Exception:
+                pass
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(lib, name)          # AttributeError here = header/library mismatch

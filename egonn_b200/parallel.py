@@ -8,10 +8,54 @@ B200 box, gloo in the CPU tests).  Local descriptors / keypoints stay on the ran
 """
 from __future__ import annotations
 
-from typing import Dict, List, Sequence, Tuple
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
+
+
+class Communicator:
+    """The engine's own NCCL communicator (``egn_comm_*`` / ``egn_allgather_global`` of the C ABI): one per process,
+    on the process's GPU.  ``torch.distributed`` is used once, as the out-of-band channel that carries rank 0's
+    128-byte NCCL id to the other ranks; the all-gather itself is issued by the library on the caller's CUDA stream
+    (no PyTorch collective, no cross-stream coupling through PyTorch's internal NCCL stream)."""
+
+    def __init__(self, device: torch.device, group=None):
+        from . import lib as L
+        assert dist.is_initialized(), "init torch.distributed first (it only carries the NCCL id)"
+        self.lib = L.load()
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.device = torch.device(device)
+        ident = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            L.check(self.lib.egn_comm_unique_id(ident))
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        self._comm = C.c_void_p()
+        L.check(self.lib.egn_comm_create(C.byref(self._comm), self.device.index or 0, self.rank, self.world, ident))
+
+    def all_gather(self, send: torch.Tensor, recv: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """recv (world * n, D) <- send (n, D) of every rank, rank order, on the current CUDA stream."""
+        from . import lib as L
+        assert send.is_cuda and send.dtype == torch.float32 and send.is_contiguous()
+        if recv is None:
+            recv = torch.empty((self.world * send.shape[0],) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+        L.check(self.lib.egn_allgather_global(self._comm, C.c_void_p(send.data_ptr()), C.c_void_p(recv.data_ptr()), send.numel(),
+                                              C.c_void_p(torch.cuda.current_stream(send.device).cuda_stream)))
+        return recv
+
+    def close(self):
+        if getattr(self, "_comm", None) is not None and self._comm.value:
+            self.lib.egn_comm_destroy(self._comm)
+            self._comm = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def shard_clouds(sizes: Sequence[int], world_size: int) -> List[List[int]]:
@@ -27,10 +71,12 @@ def shard_clouds(sizes: Sequence[int], world_size: int) -> List[List[int]]:
     return [sorted(p) for p in parts]
 
 
-def gather_global(local: torch.Tensor, parts: List[List[int]], group=None) -> torch.Tensor:
+def gather_global(local: torch.Tensor, parts: List[List[int]], group=None, comm: Optional[Communicator] = None) -> torch.Tensor:
     """All-gather the per-rank (B_r, D) global descriptors and restore the original cloud order: (B, D).
-    Ranks may own different numbers of clouds: rows are padded to the largest share for the collective."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    Ranks may own different numbers of clouds: rows are padded to the largest share for the collective.
+    ``comm``: the engine's NCCL communicator (egn_allgather_global, CUDA tensors); without it the collective goes
+    through ``torch.distributed`` (the gloo CPU tests)."""
+    world = comm.world if comm is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
     total = sum(len(p) for p in parts)
     if world == 1:
         out = torch.empty((total, local.shape[1]), dtype=local.dtype, device=local.device)
@@ -40,7 +86,10 @@ def gather_global(local: torch.Tensor, parts: List[List[int]], group=None) -> to
     pad = torch.zeros((bmax, local.shape[1]), dtype=local.dtype, device=local.device)
     pad[: local.shape[0]] = local
     buf = torch.empty((world * bmax, local.shape[1]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(buf, pad, group=group)
+    if comm is not None:
+        comm.all_gather(pad, buf)
+    else:
+        dist.all_gather_into_tensor(buf, pad, group=group)
     out = torch.empty((total, local.shape[1]), dtype=local.dtype, device=local.device)
     for r, p in enumerate(parts):
         if p:
@@ -48,7 +97,8 @@ def gather_global(local: torch.Tensor, parts: List[List[int]], group=None) -> to
     return out
 
 
-def extract_sharded(model, clouds_coords: List[torch.Tensor], batched_coordinates, group=None) -> Tuple[torch.Tensor, Dict]:
+def extract_sharded(model, clouds_coords: List[torch.Tensor], batched_coordinates, group=None,
+                    comm: Optional[Communicator] = None) -> Tuple[torch.Tensor, Dict]:
     """Run ``model.forward_packed`` on this rank's share of ``clouds_coords`` (list of (Mi,3) int32 voxel coords on
     the rank's device) and return (all global descriptors (B,256) in original order, this rank's packed local outputs
     with ``cloud_ids`` = original indices of its clouds)."""
@@ -65,4 +115,5 @@ def extract_sharded(model, clouds_coords: List[torch.Tensor], batched_coordinate
     else:
         local, g = {}, torch.zeros((0, model.global_descriptor_size), device=dev)
     local["cloud_ids"] = mine
-    return gather_global(g, parts, group), local
+    local["parts"] = parts
+    return gather_global(g, parts, group, comm), local

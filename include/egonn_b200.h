@@ -20,6 +20,15 @@
  *   - rows of every coordinate map are kept in the engine's canonical order: ascending
  *     (batch, Morton(z,y,x)) - MinkowskiEngine's row order is not a contract.
  *   - there is NO CPU fallback: every entry point needs a CUDA device.
+ *   - names vs SURVEY.md 8b.3's minimum export set.  "egn_quantize_cartesian": here egn_quantize, which also does polar.
+ *     "egn_build_pyramid" + "egn_build_kernel_map": here ONE call, egn_coords_build, because the kernel maps are derived
+ *     top-down from the pyramid.  "egn_conv_fwd": here egn_conv and egn_conv_tc.  "egn_eca_gate": its building blocks
+ *     are egn_global_pool and egn_broadcast_mul, the fused gate lives inside egn_forward.  "egn_head_global" /
+ *     "egn_head_local": the global_out / desc_out arguments of egn_forward select the heads.  "egn_load_weights": the
+ *     egn_net struct + weight blob passed to egn_forward.  egn_allgather_global is exported under that name.
+ *   - polar quantisation: atan2f / sqrtf on the device may differ from the host libm by one ulp, so a point lying
+ *     exactly on a sector / ring boundary can fall into the neighbouring voxel; the policy (tests/test_gpu_parity.py)
+ *     is "identical voxel SET up to 1e-3 of the voxels"; cartesian quantisation is bit-exact.
  */
 #ifndef EGONN_B200_H
 #define EGONN_B200_H
@@ -229,6 +238,24 @@ int egn_match_mutual(egn_ctx *ctx, const float *desc_a, const float *desc_b, int
  * points_out (n,3) f32 caller-owned, *n_out = number of survivors (synchronises the stream once). */
 int egn_filter_points(egn_ctx *ctx, const float *records, int64_t n, int stride, int remove_zero, int remove_ground,
                       float ground_level, float *points_out, int64_t *n_out, egn_stream_t stream);
+
+/* ---- multi-GPU: ONE all-gather of the global descriptors -----------------------------------------------------
+ * Replaces: nothing in the reference - its evaluation loop is single-device (eval/evaluate.py:454-466).  When the clouds
+ * of a batch are sharded over the GPUs of a node (one process per GPU, egonn_b200/parallel.py), every rank extracts its
+ * own clouds and the ranks exchange the (clouds_per_rank, 256) f32 global descriptors with one NCCL all-gather over
+ * NVLink; local descriptors and keypoints stay rank-local, and there is no collective inside the network.
+ * NCCL is resolved at run time (dlopen of libnccl.so.2, or the path in EGN_NCCL_LIB); the library does not link it.
+ *   egn_comm_unique_id : rank 0 fills `id_out` (host, EGN_COMM_ID_BYTES) and hands the bytes to the other ranks by any
+ *                        out-of-band channel (torch.distributed store, MPI, a file).
+ *   egn_comm_create    : collective over all ranks (ncclCommInitRank) on `device`.
+ *   egn_allgather_global: recv (world * floats_per_rank) <- send (floats_per_rank) of every rank, in rank order;
+ *                        asynchronous on `stream`; every rank must pass the same floats_per_rank (pad uneven shards). */
+#define EGN_COMM_ID_BYTES 128
+typedef struct egn_comm egn_comm;
+int egn_comm_unique_id(void *id_out);
+int egn_comm_create(egn_comm **out, int device, int rank, int world, const void *id);
+int egn_comm_destroy(egn_comm *comm);
+int egn_allgather_global(egn_comm *comm, const float *send, float *recv, int64_t floats_per_rank, egn_stream_t stream);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------------------
  * egn_profile_enable(ctx, 1): every kernel class launched by this context is bracketed by CUDA events on its

@@ -17,16 +17,17 @@ from egonn_b200 import lib as L, synth  # noqa: E402
 dev = torch.device("cuda", 0)
 level = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 c = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+ksize = int(sys.argv[3]) if len(sys.argv) > 3 else 3          # 3: 3x3x3 at LEVEL; 2: stride-2 from LEVEL to LEVEL+1; 1: 1x1x1 at LEVEL
 params = E.ModelParams.from_dict(model="egonn", coordinates="cartesian", quantization_step=0.1)
 coords = [params.quantizer(torch.from_numpy(pc).to(dev))[0] for pc in synth.make_batch("cfg2")]
 eng = E.Engine(dev)
 info = eng.build(E.batched_coordinates(coords).contiguous())
 x = torch.randn(info.n_rows[level], c, device=dev)
-w = torch.randn(27, c, c, device=dev) * 0.05
+w = torch.randn(ksize ** 3, c, c, device=dev) * 0.05
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 for _ in range(3):
     flush.zero_()
-    eng.conv_tc(level, 3, x, w)
+    eng.conv_tc(level, ksize, x, w)
 torch.cuda.synchronize()
 buf = np.zeros((64, 8), dtype=np.int64)
 L.check(L.load().egn_debug_trace(eng._ctx, buf.ctypes.data_as(C.c_void_p)))
