@@ -102,6 +102,9 @@ int egn_ctx_create(egn_ctx **out, int device) {
   ctx->device = device;
   cudaError_t e1 = cudaMallocHost((void **)&ctx->host, sizeof(HostCounts));
   cudaError_t e2 = cudaMalloc((void **)&ctx->dev_counts, sizeof(HostCounts));
+  if (e2 == cudaSuccess) e2 = cudaMalloc((void **)&ctx->pool_counters, kPoolCounters * sizeof(int));
+  if (e2 == cudaSuccess) e2 = cudaMemset(ctx->pool_counters, 0, kPoolCounters * sizeof(int));
+  if (e2 == cudaSuccess) e2 = cudaDeviceSynchronize();     // the counters are zero before any (non-blocking) stream can use them
   if (e1 != cudaSuccess || e2 != cudaSuccess) {
     set_error("ctx_create: allocation failed");
     delete ctx;
@@ -140,6 +143,7 @@ int egn_ctx_destroy(egn_ctx *ctx) {
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->host) cudaFreeHost(ctx->host);
   if (ctx->dev_counts) cudaFree(ctx->dev_counts);
+  if (ctx->pool_counters) cudaFree(ctx->pool_counters);
   delete ctx;
   return EGN_OK;
 }

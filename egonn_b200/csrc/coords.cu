@@ -277,30 +277,48 @@ __global__ void k_nbr_top(const uint64_t *__restrict__ keys, int n, int level, i
 
 // level L from level L+1: neighbour (c + d) lives in the parent's neighbour (or the parent itself) as the
 // child with code c' ; child row = cstart + popc(mask below c').  One warp per row (lane = offset k), 108-byte coalesced
-// table rows, presence mask by ballot.
-__global__ void k_nbr_down(const uint64_t *__restrict__ keys, const int *__restrict__ up, int n,
-                           const int *__restrict__ nbr_up, const int *__restrict__ cstart_up,
-                           const uint32_t *__restrict__ cmask_up, int *__restrict__ nbr, uint32_t *__restrict__ mask27) {
+// table rows, presence mask by ballot.  Every entry is a chain of three dependent loads (row -> parent -> parent's
+// neighbour -> its child mask), so a warp walks kNbrRows rows at once: their chains overlap instead of queueing.
+constexpr int kNbrRows = 4;
+__global__ void __launch_bounds__(256) k_nbr_down(const uint64_t *__restrict__ keys, const int *__restrict__ up, int n,
+                                                  const int *__restrict__ nbr_up, const int *__restrict__ cstart_up,
+                                                  const uint32_t *__restrict__ cmask_up, int *__restrict__ nbr, uint32_t *__restrict__ mask27) {
   const int lane = threadIdx.x & 31;
   const int warps = (gridDim.x * blockDim.x) >> 5;
   const int dx = lane % 3 - 1, dy = (lane / 3) % 3 - 1, dz = lane / 9 - 1;
-  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
-    const uint32_t code = (uint32_t)(keys[r] & 7ull);
-    const int p = up[r];
-    int res = -1;
-    if (lane < 27) {
-      const int px = (int)(code & 1u) + dx, py = (int)((code >> 1) & 1u) + dy, pz = (int)((code >> 2) & 1u) + dz;
-      const int kk = ((px >> 1) + 1) + 3 * ((py >> 1) + 1) + 9 * ((pz >> 1) + 1);
-      const int q = kk == 13 ? p : nbr_up[(int64_t)p * 27 + kk];
-      if (q >= 0) {
-        const uint32_t cc = (uint32_t)(px & 1) | ((uint32_t)(py & 1) << 1) | ((uint32_t)(pz & 1) << 2);
-        const uint32_t m = cmask_up[q];
-        if ((m >> cc) & 1u) res = cstart_up[q] + __popc(m & ((1u << cc) - 1u));
-      }
-      nbr[(int64_t)r * 27 + lane] = res;
+  for (int r0 = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * kNbrRows; r0 < n; r0 += warps * kNbrRows) {
+    uint32_t code[kNbrRows], cc[kNbrRows], m[kNbrRows];
+    int p[kNbrRows], q[kNbrRows], cs[kNbrRows], kk[kNbrRows];
+#pragma unroll
+    for (int j = 0; j < kNbrRows; ++j) {
+      const int r = min(r0 + j, n - 1);
+      code[j] = (uint32_t)(keys[r] & 7ull);
+      p[j] = up[r];
     }
-    const uint32_t m = __ballot_sync(0xffffffffu, res >= 0);
-    if (lane == 0) mask27[r] = m;
+#pragma unroll
+    for (int j = 0; j < kNbrRows; ++j) {
+      const int px = (int)(code[j] & 1u) + dx, py = (int)((code[j] >> 1) & 1u) + dy, pz = (int)((code[j] >> 2) & 1u) + dz;
+      kk[j] = ((px >> 1) + 1) + 3 * ((py >> 1) + 1) + 9 * ((pz >> 1) + 1);
+      cc[j] = (uint32_t)(px & 1) | ((uint32_t)(py & 1) << 1) | ((uint32_t)(pz & 1) << 2);
+      q[j] = (lane < 27 && kk[j] != 13) ? nbr_up[(int64_t)p[j] * 27 + kk[j]] : p[j];
+    }
+#pragma unroll
+    for (int j = 0; j < kNbrRows; ++j) {
+      const int qq = q[j] >= 0 ? q[j] : 0;
+      m[j] = cmask_up[qq];
+      cs[j] = cstart_up[qq];
+    }
+#pragma unroll
+    for (int j = 0; j < kNbrRows; ++j) {
+      const int r = r0 + j;
+      int res = -1;
+      if (lane < 27 && q[j] >= 0 && ((m[j] >> cc[j]) & 1u)) res = cs[j] + __popc(m[j] & ((1u << cc[j]) - 1u));
+      const uint32_t mm = __ballot_sync(0xffffffffu, res >= 0);
+      if (r < n) {
+        if (lane < 27) nbr[(int64_t)r * 27 + lane] = res;
+        if (lane == 0) mask27[r] = mm;
+      }
+    }
   }
 }
 
@@ -315,7 +333,7 @@ __global__ void k_nbr_down(const uint64_t *__restrict__ keys, const int *__restr
 //                              owning a rare offset are isolated in few tiles;
 //   kind 1 (2x2x2 stride 2):   output (parent) rows sorted by their 8-bit child mask;
 //   kind 2 (transposed 2x2x2): output (fine) rows sorted by their own child code (each row uses exactly one kernel slice).
-// Rows are only re-grouped inside windows of W (4096 by default) canonical rows - one CTA sorts one window in shared
+// Rows are only re-grouped inside windows of W (8192 by default) canonical rows - one CTA sorts one window in shared
 // memory (stable radix sort, deterministic) - so a tile still gathers from a compact neighbourhood.  The maps themselves stay in canonical order: only the tile -> row assignment changes.
 constexpr int kOrderThreads = 1024;
 constexpr int kMaxOrderJobs = 3 * P;
@@ -644,11 +662,11 @@ static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64
              k_nbr_top<<<grid_for((int64_t)py.n[T] * 32, 256), 256, 0, s>>>(py.keys[T], py.n[T], T, py.nbr[T], py.mask27[T]));
   for (int L = T - 1; L >= 1; --L)
     EGN_LAUNCH(ctx, "kernel_map_3x3x3", (double)py.n[L] * (8 + 108), 0, s,
-               k_nbr_down<<<grid_for((int64_t)py.n[L] * 32, 256), 256, 0, s>>>(py.keys[L], py.up[L], py.n[L], py.nbr[L + 1],
+               k_nbr_down<<<grid_for((int64_t)div_up(py.n[L], kNbrRows) * 32, 256, 16), 256, 0, s>>>(py.keys[L], py.up[L], py.n[L], py.nbr[L + 1],
                                                                                  py.cstart[L + 1], py.cmask[L + 1], py.nbr[L], py.mask27[L]));
   EGN_CUDA(cudaGetLastError());
   if (ctx->use_order) {   // tile row orders of every level: ONE launch, one CTA per window of kOrderWindow rows
-    const int kOrderWindow = (ctx->order_window == 2048 || ctx->order_window == 8192) ? ctx->order_window : 4096;
+    const int kOrderWindow = (ctx->order_window == 2048 || ctx->order_window == 4096) ? ctx->order_window : 8192;
     OrderJobs oj;
     oj.n_jobs = 0;
     int blocks = 0;
@@ -666,12 +684,12 @@ static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64
     if (kOrderWindow == 2048) {
       EGN_SMEM_OPTIN(ctx, k_order_windows<2048>, order_smem_bytes(2048));
       EGN_LAUNCH(ctx, "tile_row_orders", rows * 8, 0, s, k_order_windows<2048><<<blocks, kOrderThreads, order_smem_bytes(2048), s>>>(oj));
-    } else if (kOrderWindow == 8192) {
-      EGN_SMEM_OPTIN(ctx, k_order_windows<8192>, order_smem_bytes(8192));
-      EGN_LAUNCH(ctx, "tile_row_orders", rows * 8, 0, s, k_order_windows<8192><<<blocks, kOrderThreads, order_smem_bytes(8192), s>>>(oj));
-    } else {
+    } else if (kOrderWindow == 4096) {
       EGN_SMEM_OPTIN(ctx, k_order_windows<4096>, order_smem_bytes(4096));
       EGN_LAUNCH(ctx, "tile_row_orders", rows * 8, 0, s, k_order_windows<4096><<<blocks, kOrderThreads, order_smem_bytes(4096), s>>>(oj));
+    } else {
+      EGN_SMEM_OPTIN(ctx, k_order_windows<8192>, order_smem_bytes(8192));
+      EGN_LAUNCH(ctx, "tile_row_orders", rows * 8, 0, s, k_order_windows<8192><<<blocks, kOrderThreads, order_smem_bytes(8192), s>>>(oj));
     }
     EGN_CUDA(cudaGetLastError());
     py.ordered = true;

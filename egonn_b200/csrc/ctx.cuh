@@ -8,6 +8,7 @@
 namespace egn {
 
 constexpr int P = EGN_PYR_LEVELS;  // pyramid levels 0..P-1
+constexpr int kPoolCounters = 1024; // clouds per batch that the single-launch poolings (ops.cu: PoolTail) can count
 
 struct Pyramid {
   bool valid = false;
@@ -78,11 +79,12 @@ struct egn_ctx {
   egn::Pyramid pyr;
   egn::HostCounts *host = nullptr;  // pinned
   int *dev_counts = nullptr;        // device mirror of HostCounts
+  int *pool_counters = nullptr;     // [kPoolCounters] "slices of cloud b finished" counters of the single-launch poolings (zero between launches)
   egn::Taps taps;
   egn::Prof prof;
   bool use_tc = true;
   bool use_order = true;            // mask-sorted tile row orders for the tensor-core convolutions (EGN_ORDER=0 disables)
-  int order_window = 4096;          // rows are re-grouped inside windows of this many canonical rows (EGN_ORDER_WINDOW = 2048 | 4096 | 8192)
+  int order_window = 8192;          // rows are re-grouped inside windows of this many canonical rows (EGN_ORDER_WINDOW = 2048 | 4096 | 8192)
   // kernels already opted in to > 48 KB dynamic shared memory ON THIS CONTEXT'S DEVICE: the attribute is per device, a
   // context belongs to one device, so the bookkeeping lives here and not in process-wide statics (egn_smem_optin below)
   std::unordered_set<const void *> smem_optin;

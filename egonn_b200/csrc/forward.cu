@@ -169,12 +169,13 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
     EGN_TRY(F.layer(net->desc_mlp[1], lvl, 1, 0, Map{d1, false}, 0, 0, Map{d2, false}));
     EGN_TRY(run_l2norm(ctx, d2, (int)n, net->desc_mlp[1].cout, desc_out, ls));
     if (net->kpsig_mlp[0].cin) {                            // fused regressors: one 64 -> 32+32 layer, one (32+32) -> 3+1 layer
-      EGN_CHECK(net->kpsig_mlp[1].cout == 4, EGN_ERR_INVALID, "fused keypoint/sigma regressor must end in 3+1 outputs");
-      float *h1 = F.alloc(n * net->kpsig_mlp[0].cout), *o4 = F.alloc(n * 4);
+      const int so = net->kpsig_mlp[1].cout;                // 3 + 1 outputs, zero-padded to a tensor-core width (32) by weights.py
+      EGN_CHECK(so >= 4, EGN_ERR_INVALID, "fused keypoint/sigma regressor must end in 3+1 outputs");
+      float *h1 = F.alloc(n * net->kpsig_mlp[0].cout), *o4 = F.alloc(n * (size_t)so);
       EGN_CHECK(h1 && o4, EGN_ERR_STATE, "feature arena exhausted (local mlps)");
       EGN_TRY(F.layer(net->kpsig_mlp[0], lvl, 1, 0, Map{lm, false}, 1, 0, Map{h1, false}));
       EGN_TRY(F.layer(net->kpsig_mlp[1], lvl, 1, 0, Map{h1, false}, 0, 0, Map{o4, false}));
-      EGN_TRY(run_kp_sigma(ctx, lvl, o4, 4, o4 + 3, 4, net->polar, net->quant_step, net->ignore_keypoint_regressor, kp_out, sigma_out, ls));
+      EGN_TRY(run_kp_sigma(ctx, lvl, o4, so, o4 + 3, so, net->polar, net->quant_step, net->ignore_keypoint_regressor, kp_out, sigma_out, ls));
     } else {
       float *k1 = F.alloc(n * net->kp_mlp[0].cout), *k2 = F.alloc(n * net->kp_mlp[1].cout);
       float *s1 = F.alloc(n * net->sigma_mlp[0].cout), *s2 = F.alloc(n * net->sigma_mlp[1].cout);

@@ -330,9 +330,23 @@ __global__ void k_gather_rows1(const float *__restrict__ in, const int *__restri
 // mode 0: sum x ; 1: sum clamp(x, eps)^p (GeM) ; 2: max x
 // CTA (b, s): 256 threads = (256 / c4) row lanes x c4 float4 column groups; every row lane walks its rows of the slice
 // with 16-byte loads, the row lanes are then added in fixed order through shared memory (deterministic).
+// Tail (single-launch pooling): the LAST CTA of cloud b to finish (device counter, self-resetting) adds the cloud's slice
+// partials in fixed order and applies the final operator - tail 1: mean / GeM root / max -> out (B,c); tail 2: the ECA gate
+// sigmoid(Conv1d_k(mean)) -> out (B,c).  Which CTA is last varies, what it computes does not: deterministic.
+struct PoolTail {
+  int kind;            // 0 none (partials only), 1 pooled value, 2 ECA gate
+  int *counter;        // [B], zero between launches
+  float *out;          // (B, c)
+  const float *wk;     // ECA Conv1d taps
+  int k;
+};
+__device__ __forceinline__ void reduce_slices(const float *__restrict__ part, int b, int c, int slices, bool is_max, float *s_tot);
+
 __global__ void __launch_bounds__(256) k_pool_partial(const float *__restrict__ x, const int *__restrict__ boff, int c, int slices, int mode,
-                                                      float p, float eps, float *__restrict__ part /* (B, slices, c) */) {
+                                                      float p, float eps, float *__restrict__ part /* (B, slices, c) */, PoolTail tail) {
   __shared__ float4 s_acc[256];
+  __shared__ float s_mean[256];
+  __shared__ int s_last;
   const int b = blockIdx.x, s = blockIdx.y;
   const int r0 = boff[b], r1 = boff[b + 1];
   const int len = r1 - r0;
@@ -362,6 +376,44 @@ __global__ void __launch_bounds__(256) k_pool_partial(const float *__restrict__ 
     }
     *(float4 *)(part + ((size_t)b * slices + s) * c + 4 * threadIdx.x) = t;
   }
+  if (tail.kind == 0) return;
+  __threadfence();                                          // this CTA's partial is visible device-wide ...
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int prev = atomicAdd(tail.counter + b, 1);        // ... before it is counted
+    s_last = prev == slices - 1;
+    if (s_last) tail.counter[b] = 0;                        // self-resetting: zero again for the next launch on this stream
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  float *s_tot = (float *)s_acc;                            // [256] (s_acc is dead)
+  reduce_slices(part, b, c, slices, mode == 2, s_tot);
+  if (tail.kind == 1) {
+    if ((int)threadIdx.x < c) {
+      const float acc = s_tot[threadIdx.x];
+      float r;
+      if (len == 0) r = 0.f;
+      else if (mode == 0) r = acc / (float)len;
+      else if (mode == 1) r = powf(acc / (float)len, 1.0f / p);
+      else r = acc;
+      tail.out[(size_t)b * c + threadIdx.x] = r;
+    }
+    return;
+  }
+  // ECA gate (layers/eca_block.py:21-31): mean -> Conv1d(1,1,k, zero pad, no bias) over channels -> sigmoid
+  if ((int)threadIdx.x < c) s_mean[threadIdx.x] = len ? s_tot[threadIdx.x] / (float)len : 0.f;
+  __syncthreads();
+  const int pad = (tail.k - 1) / 2;
+  if ((int)threadIdx.x < c) {
+    const int ch = threadIdx.x;
+    float y = 0.f;
+    for (int j = 0; j < tail.k; ++j) {
+      const int cc = ch + j - pad;
+      if (cc >= 0 && cc < c) y = fmaf(tail.wk[j], s_mean[cc], y);
+    }
+    tail.out[(size_t)b * c + ch] = 1.f / (1.f + expf(-y));
+  }
 }
 // sum (or max) of the per-slice partials of cloud b (c <= 256 channels): 256 threads = (256 / c) slice lanes x c channels, the
 // lanes are then combined in fixed order through shared memory (deterministic); result in s_tot[ch]
@@ -371,7 +423,7 @@ __device__ __forceinline__ void reduce_slices(const float *__restrict__ part, in
   float acc = is_max ? -INFINITY : 0.f;
   if (l < lanes)
     for (int s = l; s < slices; s += lanes) {
-      const float v = part[((size_t)b * slices + s) * c + ch];
+      const float v = __ldcg(part + ((size_t)b * slices + s) * c + ch);   // L2: other CTAs of this launch wrote it (fused tail)
       acc = is_max ? fmaxf(acc, v) : acc + v;
     }
   s_tot[threadIdx.x] = acc;
@@ -722,8 +774,15 @@ int run_pool(egn_ctx *ctx, int level, int c, const float *in, int mode, float p,
   const int B = py.n_batches;
   const int threads = c >= 256 ? 256 : (c < 32 ? 32 : c);
   EGN_CHECK((c & 3) == 0 && c <= 1024 && ((uintptr_t)in & 15) == 0, EGN_ERR_INVALID, "pooling: channels must be a multiple of 4 (<= 1024), 16-byte aligned rows");
+  if (c <= 256 && B <= kPoolCounters) {                     // one launch: the last CTA of every cloud finishes it
+    PoolTail tail = {1, ctx->pool_counters, out, nullptr, 0};
+    EGN_LAUNCH(ctx, "global_pool", (double)py.n[level] * c * 4 + (double)B * (slices + 1) * c * 4, 0, s,
+               k_pool_partial<<<dim3(B, slices), 256, 0, s>>>(in, py.boff[level], c, slices, mode, p, eps, part, tail));
+    EGN_CUDA(cudaGetLastError());
+    return EGN_OK;
+  }
   EGN_LAUNCH(ctx, "global_pool", (double)py.n[level] * c * 4, 0, s,
-             k_pool_partial<<<dim3(B, slices), 256, 0, s>>>(in, py.boff[level], c, slices, mode, p, eps, part));
+             k_pool_partial<<<dim3(B, slices), 256, 0, s>>>(in, py.boff[level], c, slices, mode, p, eps, part, PoolTail{0, nullptr, nullptr, nullptr, 0}));
   EGN_LAUNCH(ctx, "global_pool", (double)B * (slices + 1) * c * 4, 0, s,
              k_pool_final<<<B, 256, 0, s>>>(part, py.boff[level], c, slices, mode, p, out));
   EGN_CUDA(cudaGetLastError());
@@ -881,9 +940,16 @@ int run_eca_gate(egn_ctx *ctx, int level, int c, const float *t, const float *wk
   const Pyramid &py = ctx->pyr;
   const int threads = c >= 256 ? 256 : (c < 32 ? 32 : c);
   EGN_CHECK((c & 3) == 0 && c <= 1024, EGN_ERR_INVALID, "eca: channels must be a multiple of 4 (<= 1024)");
-  EGN_LAUNCH(ctx, "eca_pool", (double)py.n[level] * c * 4, 0, s,
-             k_pool_partial<<<dim3(py.n_batches, slices), 256, 0, s>>>(t, py.boff[level], c, slices, 0, 1.f, 0.f, part));
   EGN_CHECK(c <= 256, EGN_ERR_INVALID, "eca: at most 256 channels");
+  if (py.n_batches <= kPoolCounters) {                      // pooling + gate in ONE launch (the last CTA of a cloud computes its gate)
+    PoolTail tail = {2, ctx->pool_counters, gate, wk, k};
+    EGN_LAUNCH(ctx, "eca_pool_gate", (double)py.n[level] * c * 4 + (double)py.n_batches * (slices + 1) * c * 4, 0, s,
+               k_pool_partial<<<dim3(py.n_batches, slices), 256, 0, s>>>(t, py.boff[level], c, slices, 0, 1.f, 0.f, part, tail));
+    EGN_CUDA(cudaGetLastError());
+    return EGN_OK;
+  }
+  EGN_LAUNCH(ctx, "eca_pool", (double)py.n[level] * c * 4, 0, s,
+             k_pool_partial<<<dim3(py.n_batches, slices), 256, 0, s>>>(t, py.boff[level], c, slices, 0, 1.f, 0.f, part, PoolTail{0, nullptr, nullptr, nullptr, 0}));
   EGN_LAUNCH(ctx, "eca_gate", (double)py.n_batches * (slices + 1) * c * 4, 0, s,
              k_eca_gate<<<py.n_batches, 256, 0, s>>>(part, py.boff[level], c, slices, wk, k, gate));
   EGN_CUDA(cudaGetLastError());

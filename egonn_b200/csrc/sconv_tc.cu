@@ -28,8 +28,8 @@ __global__ void k_splitk_finish(const float4 *__restrict__ part, int splits, int
 }  // namespace tc
 
 bool sconv_tc_supported(int ksize, int transposed, int cin, int cout) {
-  if (ksize == 1) return !transposed && ((cin == 32 && cout == 64) || (cin == 64 && (cout == 64 || cout == 128)) ||
-                                         (cin == 128 && (cout == 64 || cout == 128)));
+  if (ksize == 1) return !transposed && ((cin == 32 && cout == 64) || (cin == 64 && (cout == 32 || cout == 64 || cout == 128)) ||
+                                         (cin == 128 && (cout == 64 || cout == 128 || cout == 256)) || (cin == 256 && cout == 256));
   if (transposed) return ksize == 2 && cin == cout && (cin == 32 || cin == 64 || cin == 128);
   if (ksize == 3) return (cin == 32 && (cout == 32 || cout == 64)) || (cin == 64 && (cout == 64 || cout == 128)) || (cin == 128 && cout == 128);
   if (ksize == 2) return cin == cout && (cin == 32 || cin == 64 || cin == 128);
@@ -39,7 +39,7 @@ bool sconv_tc_supported(int ksize, int transposed, int cin, int cout) {
 // packed-weight bytes for a (ksize, cin, cout) convolution: n_chunks * 2 images * cout * 128
 size_t sconv_tc_wpack_bytes(int ksize, int cin, int cout) {
   const int koff = ksize == 3 ? 27 : (ksize == 2 ? 8 : 1);
-  return (size_t)((koff * cin + 63) / 64) * 2 * cout * 128;
+  return (size_t)((koff * cin + 63) / 64) * 2 * cout * 128;     // (a 256-channel row-wise layer: koff 1 x cin 256 == 2 x 128)
 }
 
 // sconv_ts.cu: the TMEM-resident-A kernels
@@ -120,6 +120,12 @@ int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, 
       }
       return EGN_OK;
     }
+  }
+  if (ksize == 1 && (cin > 128 || cout > 128)) {
+    // wide row-wise layers (the global descriptor decoder 128 -> 192 -> 256, padded to 256): output channels N-split over
+    // grid.y CTAs of 128, a 256-channel input as two 128-channel "offsets" of the same row
+    EGN_CHECK(!in_split && !out_split, EGN_ERR_INVALID, "wide row-wise layers read and write fp32 maps");
+    return launch_conv_ts(ctx, cin / 128, 128, 128, a, name, bytes, flops, s);
   }
   return launch_conv_ts(ctx, K, cin, cout, a, name, bytes, flops, s);
 }

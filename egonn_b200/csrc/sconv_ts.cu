@@ -53,7 +53,9 @@ struct Cfg {
 // table, 2 2x2x2 stride-2 children, 3 transposed 2x2x2 (parent row, kernel slice = the row's own child code).
 template <int CIN, int COUT, int KOFF, bool SPLIT_IN, int MODE>
 __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCtasPerSm) k_sconv_ts(Args a) {
-  static_assert((MODE == 0 && KOFF == 1) || (MODE == 1 && KOFF == 27) || ((MODE == 2 || MODE == 3) && KOFF == 8), "mode / offsets");
+  // MODE 0 with KOFF == 2: a row-wise layer with 2 * CIN input channels - "offset" k reads channel block k of the same row
+  // (the (n, 2 CIN) map viewed as (2 n, CIN): source row 2 r + k).
+  static_assert((MODE == 0 && (KOFF == 1 || KOFF == 2)) || (MODE == 1 && KOFF == 27) || ((MODE == 2 || MODE == 3) && KOFF == 8), "mode / offsets");
   using C = Cfg<CIN, COUT>;
   constexpr int kStages = C::kStages, NG = C::kGroups;
   constexpr int NPW = C::kProducerWarps, NT = C::kThreads;
@@ -100,7 +102,10 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     }
     if constexpr (MODE == 0) {
 #pragma unroll
-      for (int it = 0; it < NBR_ITERS; ++it) src[it] = rowv[it];
+      for (int it = 0; it < NBR_ITERS; ++it) {
+        const int t = tid + it * NT;
+        src[it] = rowv[it] >= 0 ? rowv[it] * KOFF + (t - (t / KOFF) * KOFF) : -1;
+      }
     } else if constexpr (MODE == 1) {
 #pragma unroll
       for (int it = 0; it < NBR_ITERS; ++it) {
@@ -470,6 +475,8 @@ int launch_conv_ts(egn_ctx *ctx, int koff, int cin, int cout_cta, const tcx::Arg
   EGN_TS_CASE(8, 128, 128)
   EGN_TS_CASE(8, 128, 64)
   EGN_TS_CASE(8, 128, 32)
+  EGN_TS_CASE(2, 128, 128)
+  EGN_TS_CASE(1, 64, 32)
   EGN_TS_CASE(1, 32, 64)
   EGN_TS_CASE(1, 64, 64)
   EGN_TS_CASE(1, 64, 128)

@@ -38,7 +38,7 @@ def _bn_fold(sd, prefix, eps=1e-5):
 
 
 TC_SHAPES = {27: {(32, 32), (32, 64), (64, 64), (64, 128), (128, 128)}, 8: {(32, 32), (64, 64), (128, 128)},
-             1: {(32, 64), (64, 64), (64, 128), (128, 64), (128, 128)},
+             1: {(32, 64), (64, 32), (64, 64), (64, 128), (128, 64), (128, 128), (128, 256), (256, 256)},
              125: {(1, 32)}}          # conv0 5x5x5 with all-ones features: presence matrix x kernel (conv0_tc.cu)
 
 
@@ -158,6 +158,11 @@ def pack_egonn(sd: Dict[str, torch.Tensor], quantizer_desc: dict, global_levels=
     net.global_head = _head(blob, sd, "global_head", list(global_levels), gc)
     net.global_mlp[0] = _linear(blob, sd, "global_descriptor_decoder.net.0")
     net.global_mlp[1] = _linear(blob, sd, "global_descriptor_decoder.net.2")
+    # tensor-core form of the global decoder (models/minkgl.py:207-225, 128 -> 192 -> 256): hidden width padded 192 -> 256
+    ghid, gout = net.global_mlp[0].cout, net.global_mlp[1].cout
+    if (gc, 256) in TC_SHAPES[1] and ghid <= 256 and gout == 256:
+        net.global_mlp[0] = _linear(blob, sd, "global_descriptor_decoder.net.0", pad_out=256)
+        net.global_mlp[1] = _linear(blob, sd, "global_descriptor_decoder.net.2", pad_in=256)
     net.pool_method = 0
     net.gem_p = float(sd["global_pooling.pooling.p"].reshape(-1)[0])
     net.gem_eps = 1e-6
@@ -186,7 +191,7 @@ def pack_egonn(sd: Dict[str, torch.Tensor], quantizer_desc: dict, global_levels=
             w1[hk:, 3:] = f32(sw1).t()
             b1 = torch.cat([f32(sd["local_keypoint_regressor.net.2.linear.bias"]), f32(sd["local_sigma_regressor.net.2.linear.bias"])])
             net.kpsig_mlp[0] = _dense(blob, w0, b0)
-            net.kpsig_mlp[1] = _dense(blob, w1, b1)
+            net.kpsig_mlp[1] = _dense(blob, w1, b1, pad_out=32 if (hk + hs, 32) in TC_SHAPES[1] else 0)   # 3+1 outputs in a 32-wide tile
     net.polar = 1 if quantizer_desc["coordinates"] == "polar" else 0
     step = quantizer_desc["step"]
     step = list(step) if isinstance(step, (list, tuple)) else [step, step, step]

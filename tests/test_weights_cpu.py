@@ -67,10 +67,25 @@ def test_padded_and_fused_mlp_layers_compute_the_reference_mlps(weights):
 
     w0, b0 = _blob_layer(blob, net.kpsig_mlp[0])
     w1, b1 = _blob_layer(blob, net.kpsig_mlp[1])
-    assert (net.kpsig_mlp[0].cin, net.kpsig_mlp[0].cout, net.kpsig_mlp[1].cin, net.kpsig_mlp[1].cout) == (64, 64, 64, 4)
+    # the 3 + 1 outputs sit in a 32-wide (tensor-core) tile; columns 4.. are exact zeros
+    assert (net.kpsig_mlp[0].cin, net.kpsig_mlp[0].cout, net.kpsig_mlp[1].cin, net.kpsig_mlp[1].cout) == (64, 64, 64, 32)
+    assert net.kpsig_mlp[0].wtc >= 0 and net.kpsig_mlp[1].wtc >= 0
     got = torch.relu(x @ w0 + b0) @ w1 + b1
     torch.testing.assert_close(got[:, :3], ref_mlp("local_keypoint_regressor"), rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(got[:, 3:], ref_mlp("local_sigma_regressor"), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(got[:, 3:4], ref_mlp("local_sigma_regressor"), rtol=1e-5, atol=1e-6)
+    assert torch.all(got[:, 4:] == 0)
+
+    # global decoder 128 -> 192 -> 256 padded to 128 -> 256 -> 256 (models/minkgl.py:207-225), both layers on tensor cores
+    g0, g1 = net.global_mlp[0], net.global_mlp[1]
+    assert (g0.cin, g0.cout, g1.cin, g1.cout) == (128, 256, 256, 256) and g0.wtc >= 0 and g1.wtc >= 0
+    xg = torch.randn(40, 128)
+    w0, b0 = _blob_layer(blob, g0)
+    w1, b1 = _blob_layer(blob, g1)
+    p = "global_descriptor_decoder"
+    ref = torch.relu(xg @ weights[p + ".net.0.linear.weight"].t() + weights[p + ".net.0.linear.bias"]) @ \
+        weights[p + ".net.2.linear.weight"].t() + weights[p + ".net.2.linear.bias"]
+    torch.testing.assert_close(torch.relu(xg @ w0 + b0) @ w1 + b1, ref, rtol=1e-5, atol=1e-5)
+    assert torch.all(torch.relu(xg @ w0 + b0)[:, 192:] == 0)
 
 
 def test_batchnorm_fold_matches_torch(weights):
