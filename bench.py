@@ -17,6 +17,12 @@ KITTI-64-beam-shaped clouds, 0.10 m voxels, per GPU: weak scaling).
   roofline     : dominant kernel class by device time (live CUDA-event brackets inside the engine).
   cpu_baseline : the ME-semantics CPU oracle (oracle/, torch CPU, all host threads) on a bounded sample.
 --impl reference times that CPU oracle as the reference arm (MinkowskiEngine itself cannot be installed).
+
+Multi-GPU (torchrun, one process per GPU): weak scaling by default (every rank extracts its own --batch clouds); the ONE
+collective of the path - the all-gather of the (clouds, 256) global descriptors - is issued through the engine's own
+NCCL communicator (egn_allgather_global, one communicator per CUDA stream) on the step's stream.  --strong runs the
+config's TOTAL batch (cfg4: 256 clouds) sharded over the ranks by egonn_b200.parallel (greedy balance by voxel count,
+original order restored after the gather); --no-gather is the ablation that drops the collective.
 """
 from __future__ import annotations
 
@@ -168,6 +174,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=3, help="concurrent CUDA streams / engine contexts per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the config's total batch sharded over the ranks (egonn_b200.parallel)")
+    ap.add_argument("--no-gather", action="store_true", help="ablation: skip the all-gather of global descriptors")
     ap.add_argument("--profile-out", default=None, help="write the per-kernel-class table (JSON) here")
     args = ap.parse_args()
 
@@ -189,29 +197,55 @@ def main():
     K = args.steps
     batch = args.batch or synth.CONFIGS[args.config]["batch"]
 
+    from egonn_b200 import parallel
     sd, wdesc = load_weights()
-    clouds, voxel, desc = make_workload(args.config, batch, rank)
+    voxel = synth.CONFIGS[args.config]["voxel"]
     params = E.ModelParams.from_dict(model="egonn", coordinates="cartesian", quantization_step=voxel)
     model = E.model_factory(params)
     model.load_state_dict(sd)
     model = model.eval().to(dev)
-
-    # ---- device-resident voxelised batch (the `value` arm) ----
-    coords = [params.quantizer(torch.from_numpy(pc).to(dev))[0] for pc in clouds]
-    bcoords = E.batched_coordinates(coords).contiguous()
-    feats = torch.ones((bcoords.shape[0], 1), device=dev)
-    gathered = torch.empty((world * batch, 256), device=dev) if world > 1 else None
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # 256 MiB > 126 MB L2
-
     S = max(1, args.streams)
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    do_gather = world > 1 and not args.no_gather
+    # one engine-owned NCCL communicator per stream: steps on different streams never share (or reorder) a communicator
+    comms = [parallel.Communicator(dev) for _ in range(S)] if do_gather else []
+    comm_of = {st.cuda_stream: c for st, c in zip(streams, comms)}
+
+    # ---- device-resident voxelised batch (the `value` arm) ----
+    imbalance = None
+    if args.strong:
+        # strong scaling (BASELINE config 4): the config's whole batch, sharded over the ranks by voxel count
+        total = synth.CONFIGS[args.config]["batch"] if args.batch is None else args.batch
+        desc = synth.CONFIGS[args.config]["desc"]
+        all_clouds = synth.make_batch(args.config, batch=total)
+        all_coords = [params.quantizer(torch.from_numpy(pc).to(dev))[0] for pc in all_clouds]
+        sb = parallel.ShardedBatch(all_coords, E.batched_coordinates, rank, world)
+        imbalance = sb.imbalance
+        clouds = [all_clouds[i] for i in sb.mine]
+        bcoords, feats, batch = sb.coords, sb.features, len(sb.mine)
+        clouds_total = total
+        del all_coords
+    else:
+        clouds, voxel, desc = make_workload(args.config, batch, rank)
+        coords = [params.quantizer(torch.from_numpy(pc).to(dev))[0] for pc in clouds]
+        bcoords = E.batched_coordinates(coords).contiguous()
+        feats = torch.ones((bcoords.shape[0], 1), device=dev)
+        clouds_total = world * batch
+        sb = None
+    gathered = [torch.empty((world * batch, 256), device=dev) for _ in range(S)] if do_gather and not args.strong else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # 256 MiB > 126 MB L2
 
     def step_device():
-        p = model.forward_packed({"coords": bcoords, "features": feats})
+        cur = torch.cuda.current_stream().cuda_stream
+        if args.strong:
+            g_all, p = parallel.run_sharded(model, sb, comm=comm_of.get(cur)) if do_gather else (None, model.forward_packed({"coords": bcoords, "features": feats}))
+        else:
+            p = model.forward_packed({"coords": bcoords, "features": feats})
+            if do_gather:
+                comm_of[cur].all_gather(p["global"], gathered[streams_index[cur]])
         idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, p["global"])
         return p, idx
+    streams_index = {st.cuda_stream: i for i, st in enumerate(streams)}
 
     def run_device(n_steps, do_flush=True):
         """n_steps steps round-robin over S streams (one engine context each): a batch's small upper pyramid levels
@@ -238,17 +272,23 @@ def main():
     # ---- host-resident raw clouds (the `e2e` arm): pinned host points -> H2D -> fused quantise+pyramid -> forward ->
     #      top-k -> D2H of global descriptors, top-256 keypoints and their descriptors.  Two device slots: the H2D of step
     #      i+1 (copy stream) overlaps the compute of step i; every byte of every step moves inside the timed region. ----
-    host_pts = [torch.from_numpy(pc).pin_memory() for pc in clouds]
-    starts = np.cumsum([0] + [t.shape[0] for t in host_pts]).astype(np.int32)
-    off_host = torch.from_numpy(starts).pin_memory()
-    h2d_bytes = sum(t.numel() * 4 for t in host_pts) + off_host.numel() * 4
+    #      ONE pinned staging buffer per direction: [points of all clouds | first-point offsets] goes up in one copy, the
+    #      packed [global | keypoints | descriptors] rows of all clouds (egn_pack_topk) come down in one copy.
+    n_pts = int(sum(pc.shape[0] for pc in clouds))
+    starts = np.cumsum([0] + [pc.shape[0] for pc in clouds]).astype(np.int32)
+    stage_words = n_pts * 3 + batch + 1
+    host_in = torch.empty((stage_words,), dtype=torch.float32).pin_memory()
+    host_in[: n_pts * 3] = torch.from_numpy(np.concatenate(clouds, axis=0).reshape(-1))
+    host_in[n_pts * 3:] = torch.from_numpy(starts).view(torch.float32)
+    h2d_bytes = stage_words * 4
     NS = max(2, S)                                        # device slots: H2D of later steps overlaps compute of earlier ones
-    dev_pts = [torch.empty((int(starts[-1]), 3), device=dev) for _ in range(NS)]
-    dev_off = [torch.empty((batch + 1,), dtype=torch.int32, device=dev) for _ in range(NS)]
-    out_g = [torch.empty((batch, 256), dtype=torch.float32).pin_memory() for _ in range(NS)]
-    out_kp = [torch.empty((batch, TOPK, 3), dtype=torch.float32).pin_memory() for _ in range(NS)]
-    out_ds = [torch.empty((batch, TOPK, 128), dtype=torch.float32).pin_memory() for _ in range(NS)]
-    d2h_bytes = (out_g[0].numel() + out_kp[0].numel() + out_ds[0].numel()) * 4
+    dev_in = [torch.empty((stage_words,), dtype=torch.float32, device=dev) for _ in range(NS)]
+    dev_pts = [t[: n_pts * 3].view(n_pts, 3) for t in dev_in]
+    dev_off = [t[n_pts * 3:].view(torch.int32) for t in dev_in]
+    per_cloud = 256 + TOPK * 3 + TOPK * 128
+    dev_out = [torch.empty((batch, per_cloud), dtype=torch.float32, device=dev) for _ in range(NS)]
+    host_out = [torch.empty((batch, per_cloud), dtype=torch.float32).pin_memory() for _ in range(NS)]
+    d2h_bytes = batch * per_cloud * 4
     copy_stream = torch.cuda.Stream(device=dev)
     ev_h2d = [torch.cuda.Event() for _ in range(NS)]
     ev_done = [torch.cuda.Event() for _ in range(NS)]
@@ -258,9 +298,7 @@ def main():
     def enqueue_h2d(slot):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(ev_done[slot])              # the previous user of this slot has finished
-            for i, t in enumerate(host_pts):
-                dev_pts[slot][int(starts[i]):int(starts[i + 1])].copy_(t, non_blocking=True)
-            dev_off[slot].copy_(off_host, non_blocking=True)
+            dev_in[slot].copy_(host_in, non_blocking=True)     # ONE host-to-device copy per step
             ev_h2d[slot].record(copy_stream)
 
     def compute_e2e(slot):
@@ -268,13 +306,14 @@ def main():
             cur = torch.cuda.current_stream()
             cur.wait_event(ev_h2d[slot])
             p = model.forward_points(dev_pts[slot], dev_off[slot])
-            idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK).long()
-            rows = (idx.clamp_min(0) + p["local_offsets"][:-1].long()[:, None])
-            out_g[slot].copy_(p["global"], non_blocking=True)
-            out_kp[slot].copy_(p["keypoints"][rows], non_blocking=True)
-            out_ds[slot].copy_(p["descriptors"][rows], non_blocking=True)
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, p["global"])
+            idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK)
+            E.pack_topk(idx, p["local_offsets"], p["keypoints"], p["descriptors"], p["global"], out=dev_out[slot])
+            host_out[slot].copy_(dev_out[slot], non_blocking=True)   # ONE device-to-host copy per step
+            if do_gather:
+                if args.strong:
+                    parallel.gather_global(p["global"], sb.parts, comm=comm_of[cur.cuda_stream])
+                else:
+                    comm_of[cur.cuda_stream].all_gather(p["global"], gathered[slot % S])
             ev_done[slot].record(cur)
 
     def run_e2e(n_steps):
@@ -304,7 +343,7 @@ def main():
     total_ms = run_device(K)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    launches = (sum(e.launch_count() for e in engines) - launches0) / K + 1        # + the top-k kernel of every step
+    launches = (sum(e.launch_count() for e in engines) - launches0) / K + 1        # + the top-k kernel of every step (NCCL's kernel not counted)
     ms_step = float(total_ms / K)
     eng = model._engine
 
@@ -318,15 +357,16 @@ def main():
     clocks = sampler.stop()
 
     # ---- per-kernel-class profile (separate pass so the event brackets do not perturb the timed region) ----
-    step_device()                                   # engine context of the default stream
-    eng = model._engine
-    eng.profile(True)
-    for _ in range(min(K, 10)):
-        flush.zero_()
+    with torch.cuda.stream(streams[0]):             # every rank: same stream, same number of steps (the collective stays in order)
         step_device()
-    torch.cuda.synchronize()
-    prof = eng.profile_read()
-    eng.profile(False)
+        eng = model._engine
+        eng.profile(True)
+        for _ in range(min(K, 10)):
+            flush.zero_()
+            step_device()
+        torch.cuda.synchronize()
+        prof = eng.profile_read()
+        eng.profile(False)
     n_prof = min(K, 10)
 
     if world > 1:
@@ -359,15 +399,18 @@ def main():
                     "alg_bytes_per_launch": top["alg_bytes"] / max(top["launches"], 1),
                     "avg_launch_ms": top["ms"] / max(top["launches"], 1)}
         voxels = int(bcoords.shape[0])
-        line = {"metric": METRIC, "value": world * batch / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        line = {"metric": METRIC, "value": clouds_total / (ms_step / 1e3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32",
                 "data": f"synthetic ({wdesc})",
                 "config": {"workload": f"{args.config}: {desc}", "clouds_per_gpu": batch, "voxels_per_gpu_step": voxels,
                            "level_rows": eng.info.n_rows[:8], "voxel_m": voxel, "topk": TOPK, "l2_flush_between_steps": True, "l2_flush_inside_timed_region": True, "streams_per_gpu": S,
                            "weights_l2_persisting": True,
-                           "parallelism": f"dp{world} over clouds" + (", 1 NCCL all-gather of global descriptors" if world > 1 else "")},
+                           "parallelism": f"dp{world} over clouds" + (", 1 NCCL all-gather of global descriptors per step (egn_allgather_global, "
+                                                                      "one communicator per stream)" if do_gather else
+                                                                      (", all-gather DISABLED (ablation)" if world > 1 else "")),
+                           "clouds_total_per_step": clouds_total, "shard_imbalance_max_over_mean": imbalance},
                 "clocks": clocks,
-                "e2e": {"value": world * batch / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "e2e": {"value": clouds_total / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                         "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes},
                 "gpu_launches": launches, "wall_ms_per_step_incl_flush": t_wall * 1e3 / K,
                 "roofline": roofline}
@@ -379,6 +422,8 @@ def main():
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        for c in comms:
+            c.close()
         dist.destroy_process_group()
 
 

@@ -13,6 +13,6 @@ from .params import ModelParams  # noqa: F401
 from .models import (model_factory, create_egonn_model, MinkGL, MinkTrunk, MinkHead, ECABasicBlock, MinkFPN,  # noqa: F401
                      MinkLoc, MinkLoc3D)
 from .quantization import CartesianQuantizer, PolarQuantizer, batched_coordinates  # noqa: F401
-from .engine import Engine, topk_smallest, knn_global, match_descriptors, filter_points  # noqa: F401
+from .engine import Engine, topk_smallest, pack_topk, knn_global, match_descriptors, filter_points  # noqa: F401
 
 __version__ = "0.1.0"

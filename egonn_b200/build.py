@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libegonn_b200.so")
-SOURCES = ["api.cu", "coords.cu", "ops.cu", "forward.cu", "sconv_tc.cu", "sconv_ts.cu", "conv0_tc.cu", "comm.cu"]
+SOURCES = ["api.cu", "coords.cu", "ops.cu", "forward.cu", "sconv_tc.cu", "sconv_ts.cu", "conv0_tc.cu", "comm.cu", "sort.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

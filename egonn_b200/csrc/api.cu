@@ -326,5 +326,9 @@ int egn_debug_trace(egn_ctx *ctx, long long *host_out) {
 int egn_topk_smallest(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out, egn_stream_t stream) {
   return op_topk(sigma, offsets, n_batches, k, idx_out, (cudaStream_t)stream);
 }
+int egn_pack_topk(const int32_t *idx, const int32_t *offsets, int n_batches, int k, const float *keypoints, const float *descriptors,
+                  int desc_dim, const float *global, int global_dim, float *out, egn_stream_t stream) {
+  return op_pack_topk(idx, offsets, n_batches, k, keypoints, descriptors, desc_dim, global, global_dim, out, (cudaStream_t)stream);
+}
 
 }  // extern "C"

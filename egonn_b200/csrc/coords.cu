@@ -11,7 +11,6 @@
 // level 0 (parent key = key >> 3), so level L row indices are prefix counts of "new run at level L" flags and
 // the child->parent map, the first-child pointer and the 8-bit child occupancy fall out of the same pass.
 // Neighbour tables are built top-down: the neighbours of a voxel are children of its parent's neighbours.
-#include <cub/device/device_radix_sort.cuh>
 
 #include "ctx.cuh"
 
@@ -504,26 +503,14 @@ __global__ void k_count_pairs_conv0(const uint64_t *__restrict__ keys0, const in
 }
 
 // ------------------------------------------------------------------------------------------------------
-static size_t sort_temp_bytes(int n, int end_bit) {
-  size_t temp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (uint64_t *)nullptr, (uint64_t *)nullptr, (uint32_t *)nullptr,
-                                  (uint32_t *)nullptr, n, 0, end_bit, (cudaStream_t)0);
-  return temp_bytes;
-}
-
-static int sort_pairs(Arena &scratch, uint64_t *kin, uint64_t *kout, uint32_t *vin, uint32_t *vout, int n, int end_bit,
-                      cudaStream_t s) {
-  size_t temp_bytes = sort_temp_bytes(n, end_bit);
-  void *temp = scratch.take(temp_bytes);
-  EGN_CHECK(temp != nullptr, EGN_ERR_STATE, "scratch arena exhausted in sort_pairs (%zu bytes)", temp_bytes);
-  EGN_CUDA(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, kin, kout, vin, vout, n, 0, end_bit, s));
-  return EGN_OK;
-}
+// sort.cu: the in-tree stable LSD radix sort (one launch per 8-bit digit)
+size_t sort_scratch_ints(int64_t n, int end_bit);
+int sort_pairs(egn_ctx *ctx, uint64_t **kin, uint64_t **kout, uint32_t **vin, uint32_t **vout, int n, int end_bit, int *hist, cudaStream_t s);
 
 static size_t sort_scratch_bytes(int64_t n) {
-  // keys in/out, vals in/out, cub temp, tile counts, profile counters
+  // keys in/out, vals in/out, the sort's count matrices, tile counts, profile counters
   const int64_t nblocks = div_up(n, kTile);
-  return pad256(n * 8) * 2 + pad256(n * 4) * 2 + pad256(sort_temp_bytes((int)n, 64)) + pad256(nblocks * P * 4) + (1 << 16);
+  return pad256(n * 8) * 2 + pad256(n * 4) * 2 + pad256(sort_scratch_ints(n, 64) * 4) + pad256(nblocks * P * 4) + (1 << 16);
 }
 
 __global__ void k_quant_pack_batch(const float *__restrict__ pts, int n, const int *__restrict__ cloud_off, int n_clouds, float q0,
@@ -586,8 +573,10 @@ static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64
   int batch_bits = 10;
   if (src.points) { batch_bits = 1; while ((1 << batch_bits) < src.n_clouds) ++batch_bits; }
   const int end_bit = narrow ? 3 * kNarrowBits + batch_bits : 64;
-  if (ctx->prof.on) ctx->prof.begin("coords_radix_sort(cub)", (double)n * 24 * ((end_bit + 7) / 8), 0, s);
-  EGN_TRY(sort_pairs(sc, kin, kout, vin, vout, n, end_bit, s));
+  int *sort_hist = (int *)sc.take(sort_scratch_ints(n, end_bit) * 4);
+  EGN_CHECK(sort_hist != nullptr, EGN_ERR_STATE, "scratch arena exhausted (sort)");
+  if (ctx->prof.on) ctx->prof.begin("coords_radix_sort", (double)n * 24 * ((end_bit + 7) / 8), 0, s);
+  EGN_TRY(sort_pairs(ctx, &kin, &kout, &vin, &vout, n, end_bit, sort_hist, s));      // kout / vout: the sorted pairs
   if (ctx->prof.on) ctx->prof.end(s);
   if (narrow) EGN_LAUNCH(ctx, "coords_expand_keys", (double)n * 16, 0, s, k_expand_keys<<<grid_for(n, 256), 256, 0, s>>>(kout, n));
   EGN_LAUNCH(ctx, "coords_level_count", (double)n * 8, 0, s, k_level_count<<<nblocks, kTileThreads, 0, s>>>(kout, n, nblocks, counts));
@@ -901,8 +890,10 @@ int quantize(egn_ctx *ctx, const float *points, int64_t n64, const float step[3]
   EGN_CUDA(cudaMemsetAsync(keep, 0, (size_t)n, s));
   EGN_LAUNCH(ctx, "quantize_pack", (double)n * 36, 0, s,
              k_quant_pack<<<grid_for(n, 256), 256, 0, s>>>(points, n, step[0], step[1], step[2], polar, vox, kin, vin, ctx->dev_counts));
-  if (ctx->prof.on) ctx->prof.begin("quantize_radix_sort(cub)", (double)n * 24 * 7, 0, s);
-  EGN_TRY(sort_pairs(sc, kin, kout, vin, vout, n, kMortonBits, s));
+  int *sort_hist = (int *)sc.take(sort_scratch_ints(n, kMortonBits) * 4);
+  EGN_CHECK(sort_hist != nullptr, EGN_ERR_STATE, "scratch arena exhausted (sort)");
+  if (ctx->prof.on) ctx->prof.begin("quantize_radix_sort", (double)n * 24 * 7, 0, s);
+  EGN_TRY(sort_pairs(ctx, &kin, &kout, &vin, &vout, n, kMortonBits, sort_hist, s));  // kout / vout: the sorted pairs
   if (ctx->prof.on) ctx->prof.end(s);
   EGN_LAUNCH(ctx, "quantize_mark_first", (double)n * 13, 0, s, k_mark_first<<<grid_for(n, 256), 256, 0, s>>>(kout, vout, n, keep));
   EGN_LAUNCH(ctx, "quantize_compact", (double)n * 2, 0, s, k_keep_count<<<nblocks, kTileThreads, 0, s>>>(keep, n, counts));

@@ -140,6 +140,8 @@ int op_knn_l2(egn_ctx *ctx, const float *query, const float *map, int Q, int M, 
 int op_match_mutual(egn_ctx *ctx, const float *a, const float *b, int na, int nb, int d, int mutual, int32_t *idx_out, float *dist_out,
                     cudaStream_t s);
 int op_topk(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out, cudaStream_t s);
+int op_pack_topk(const int32_t *idx, const int32_t *offsets, int n_batches, int k, const float *kp, const float *desc, int D,
+                 const float *glob, int G, float *out, cudaStream_t s);
 // sconv_tc.cu
 bool sconv_tc_supported(int ksize, int transposed, int cin, int cout);
 int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, int cout, const float *in, const void *wpack,

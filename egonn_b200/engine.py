@@ -305,3 +305,22 @@ def topk_smallest(sigma: torch.Tensor, offsets: torch.Tensor, k: int) -> torch.T
     out = torch.empty((nb, k), dtype=torch.int32, device=s.device)
     L.check(L.load().egn_topk_smallest(_ptr(s), _ptr(off), nb, k, _ptr(out), _stream()))
     return out
+
+
+def pack_topk(idx: torch.Tensor, offsets: torch.Tensor, keypoints: torch.Tensor, descriptors: torch.Tensor,
+              global_desc: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The selected keypoints / descriptors of every cloud next to its global descriptor (eval/evaluate.py:339-350), packed
+    as (B, G + k*3 + k*D) f32 rows [global | keypoints | descriptors] for one device-to-host copy; zeros for -1 padding."""
+    _need_cuda(idx, "idx")
+    idx = idx.to(torch.int32).contiguous()
+    off = offsets.to(torch.int32).contiguous()
+    kp = keypoints.detach().to(torch.float32).contiguous()
+    ds = descriptors.detach().to(torch.float32).contiguous()
+    nb, k = idx.shape
+    D = ds.shape[1]
+    G = 0 if global_desc is None else global_desc.shape[1]
+    g = None if global_desc is None else global_desc.detach().to(torch.float32).contiguous()
+    if out is None:
+        out = torch.empty((nb, G + k * 3 + k * D), dtype=torch.float32, device=idx.device)
+    L.check(L.load().egn_pack_topk(_ptr(idx), _ptr(off), nb, k, _ptr(kp), _ptr(ds), D, _ptr(g), G, _ptr(out), _stream()))
+    return out

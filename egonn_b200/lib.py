@@ -77,6 +77,7 @@ _SIGNATURES = {
     "egn_launch_count": (C.c_int64, [_P]),
     "egn_debug_trace": (C.c_int, [_P, _P]),
     "egn_topk_smallest": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
+    "egn_pack_topk": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, C.c_int, _P, C.c_int, _P, _P]),
     "egn_comm_unique_id": (C.c_int, [_P]),
     "egn_comm_create": (C.c_int, [C.POINTER(_P), C.c_int, C.c_int, C.c_int, _P]),
     "egn_comm_destroy": (C.c_int, [_P]),

@@ -97,23 +97,48 @@ def gather_global(local: torch.Tensor, parts: List[List[int]], group=None, comm:
     return out
 
 
+class ShardedBatch:
+    """This rank's share of a batch of voxelised clouds: the greedy partition, the batched coordinates of its clouds
+    (``ME.utils.batched_coordinates`` of the share) and the all-ones features - everything that does not change when the
+    same batch is extracted again."""
+
+    def __init__(self, clouds_coords: List[torch.Tensor], batched_coordinates, rank: int, world: int):
+        self.sizes = [int(c.shape[0]) for c in clouds_coords]
+        self.parts = shard_clouds(self.sizes, world)
+        self.mine = self.parts[rank]
+        self.device = clouds_coords[0].device
+        self.loads = [sum(self.sizes[i] for i in p) for p in self.parts]          # voxels per rank
+        if self.mine:
+            self.coords = batched_coordinates([clouds_coords[i] for i in self.mine]).contiguous()
+            self.features = torch.ones((self.coords.shape[0], 1), device=self.device)
+        else:
+            self.coords = self.features = None
+
+    @property
+    def imbalance(self) -> float:
+        """max / mean voxels per rank (1.0 = perfectly balanced)."""
+        return max(self.loads) / (sum(self.loads) / len(self.loads)) if sum(self.loads) else 1.0
+
+
+def run_sharded(model, sb: ShardedBatch, group=None, comm: Optional[Communicator] = None) -> Tuple[torch.Tensor, Dict]:
+    """Forward of this rank's share + the ONE all-gather of the path: (all global descriptors (B,256) in original cloud
+    order, this rank's packed local outputs with ``cloud_ids``)."""
+    if sb.mine:
+        local = model.forward_packed({"coords": sb.coords, "features": sb.features})
+        g = local["global"]
+    else:
+        local, g = {}, torch.zeros((0, model.global_descriptor_size), device=sb.device)
+    local["cloud_ids"] = sb.mine
+    local["parts"] = sb.parts
+    return gather_global(g, sb.parts, group, comm), local
+
+
 def extract_sharded(model, clouds_coords: List[torch.Tensor], batched_coordinates, group=None,
                     comm: Optional[Communicator] = None) -> Tuple[torch.Tensor, Dict]:
     """Run ``model.forward_packed`` on this rank's share of ``clouds_coords`` (list of (Mi,3) int32 voxel coords on
-    the rank's device) and return (all global descriptors (B,256) in original order, this rank's packed local outputs
-    with ``cloud_ids`` = original indices of its clouds)."""
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    parts = shard_clouds([int(c.shape[0]) for c in clouds_coords], world)
-    mine = parts[rank]
-    dev = clouds_coords[0].device
-    if mine:
-        bc = batched_coordinates([clouds_coords[i] for i in mine])
-        feats = torch.ones((bc.shape[0], 1), device=dev)
-        local = model.forward_packed({"coords": bc, "features": feats})
-        g = local["global"]
-    else:
-        local, g = {}, torch.zeros((0, model.global_descriptor_size), device=dev)
-    local["cloud_ids"] = mine
-    local["parts"] = parts
-    return gather_global(g, parts, group, comm), local
+    the rank's device; the single-device original is the loop of eval/evaluate.py:454-466) and return (all global
+    descriptors (B,256) in original order, this rank's packed local outputs with ``cloud_ids`` = original indices of
+    its clouds)."""
+    world = comm.world if comm is not None else (dist.get_world_size(group) if dist.is_initialized() else 1)
+    rank = comm.rank if comm is not None else (dist.get_rank(group) if dist.is_initialized() else 0)
+    return run_sharded(model, ShardedBatch(clouds_coords, batched_coordinates, rank, world), group, comm)

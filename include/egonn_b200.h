@@ -214,6 +214,14 @@ int egn_broadcast_mul(egn_ctx *ctx, int level, int c, const float *in, const flo
 int egn_topk_smallest(const float *sigma, const int32_t *offsets, int n_batches, int k, int32_t *idx_out,
                       egn_stream_t stream);
 
+/* Replaces: the per-cloud selection that follows it, eval/evaluate.py:339-350 (descriptors[ndx], keypoints[ndx] next to the
+ * cloud's global descriptor), for ALL clouds of a batch in one launch, packed for ONE device-to-host copy.
+ * idx (n_batches,k) from egn_topk_smallest, offsets (n_batches+1), keypoints (n,3), descriptors (n,desc_dim), global
+ * (n_batches, global_dim) or NULL with global_dim 0.  out (n_batches, global_dim + k*3 + k*desc_dim) f32 per cloud:
+ * [global | keypoints (k,3) | descriptors (k,desc_dim)], zeros where idx == -1. */
+int egn_pack_topk(const int32_t *idx, const int32_t *offsets, int n_batches, int k, const float *keypoints, const float *descriptors,
+                  int desc_dim, const float *global, int global_dim, float *out, egn_stream_t stream);
+
 /* Replaces: the global-descriptor nearest-neighbour search of eval/evaluate.py:173-176
  * (embed_dist = np.linalg.norm(map_embeddings - query_embedding, axis=1); nn_ndx = np.argsort(embed_dist)[:k]).
  * query (n_query, dim), map (n_map, dim) f32; idx_out (n_query, k) int32 map rows by ascending distance (ties: lower
