@@ -123,7 +123,8 @@ __global__ void __launch_bounds__(1024) k_level_scan(int *__restrict__ counts, i
   __shared__ int s_warp[32];
   __shared__ int s_carry;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int L = 0; L < P; ++L) {
+  {
+    const int L = blockIdx.x;                               // one CTA per pyramid level
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     int *row = counts + (size_t)L * nblocks;
@@ -233,18 +234,28 @@ struct BoffArgs {
   int *boff[P];
   int n[P];
 };
+// first row of every batch index at every level: one WARP per (level, batch), 32-ary search (4 probe rounds for a million
+// rows instead of 20 dependent loads)
 __global__ void k_batch_offsets(BoffArgs a, int n_batches) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int L = t / (n_batches + 1), b = t % (n_batches + 1);
   if (L >= P) return;
   const uint64_t target = (uint64_t)b << (kMortonBits - 3 * L);
-  int lo = 0, hi = a.n[L];
+  int lo = 0, hi = a.n[L];                                  // answer in [lo, hi]: first index with key >= target
   const uint64_t *k = a.keys[L];
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (k[mid] < target) lo = mid + 1; else hi = mid;
+  while (hi - lo > 0) {
+    const int span = hi - lo;
+    const int step = (span + 31) / 32;                      // lane probes lo + lane * step
+    const int i = lo + lane * step;
+    const bool below = i < hi && k[i] < target;             // keys sorted: `below` is true for a prefix of the lanes
+    const uint32_t m = __ballot_sync(0xffffffffu, below);
+    const int c = __popc(m);                                // probes [0, c) are below the target
+    if (c == 0) { hi = lo; break; }
+    const int nlo = lo + (c - 1) * step + 1;                // the last probe below the target is excluded ...
+    const int nhi = min(hi, lo + c * step);                 // ... the first probe not below it (or hi) bounds the answer
+    lo = nlo; hi = nhi;
   }
-  a.boff[L][b] = lo;
+  if (lane == 0) a.boff[L][b] = lo;
 }
 
 // 27-neighbour table of the coarsest level by binary search (a few hundred rows per cloud).  One warp per row: lane k < 27
@@ -278,7 +289,7 @@ __global__ void k_nbr_top(const uint64_t *__restrict__ keys, int n, int level, i
 // child with code c' ; child row = cstart + popc(mask below c').  One warp per row (lane = offset k), 108-byte coalesced
 // table rows, presence mask by ballot.  Every entry is a chain of three dependent loads (row -> parent -> parent's
 // neighbour -> its child mask), so a warp walks kNbrRows rows at once: their chains overlap instead of queueing.
-constexpr int kNbrRows = 4;
+constexpr int kNbrRows = 8;
 __global__ void __launch_bounds__(256) k_nbr_down(const uint64_t *__restrict__ keys, const int *__restrict__ up, int n,
                                                   const int *__restrict__ nbr_up, const int *__restrict__ cstart_up,
                                                   const uint32_t *__restrict__ cmask_up, int *__restrict__ nbr, uint32_t *__restrict__ mask27) {
@@ -580,7 +591,7 @@ static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64
   if (ctx->prof.on) ctx->prof.end(s);
   if (narrow) EGN_LAUNCH(ctx, "coords_expand_keys", (double)n * 16, 0, s, k_expand_keys<<<grid_for(n, 256), 256, 0, s>>>(kout, n));
   EGN_LAUNCH(ctx, "coords_level_count", (double)n * 8, 0, s, k_level_count<<<nblocks, kTileThreads, 0, s>>>(kout, n, nblocks, counts));
-  EGN_LAUNCH(ctx, "coords_level_scan", (double)nblocks * P * 8, 0, s, k_level_scan<<<1, 1024, 0, s>>>(counts, nblocks, ctx->dev_counts));
+  EGN_LAUNCH(ctx, "coords_level_scan", (double)nblocks * P * 8, 0, s, k_level_scan<<<P, 1024, 0, s>>>(counts, nblocks, ctx->dev_counts));
   EGN_CUDA(cudaMemcpyAsync(ctx->host, ctx->dev_counts, sizeof(HostCounts), cudaMemcpyDeviceToHost, s));
   EGN_CUDA(cudaStreamSynchronize(s));
 
@@ -589,8 +600,10 @@ static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64
     return coords_build_common(ctx, src, n64, info, s, false);
   info->n_input = n;
   info->n_batches = hc.n_batches;
-  info->status = (hc.status & 1) ? EGN_ERR_RANGE : EGN_OK;
+  info->status = (hc.status & 1) ? EGN_ERR_RANGE : ((hc.status & 4) ? EGN_ERR_INVALID : EGN_OK);
   for (int L = 0; L < P; ++L) info->n_rows[L] = hc.totals[L];
+  EGN_CHECK((hc.status & 4) == 0, EGN_ERR_INVALID,
+            "coords_build_points: cloud_offsets must start at 0, end at n and never decrease (they label every point with its cloud)");
   EGN_CHECK((hc.status & 1) == 0, EGN_ERR_RANGE,
             "coords_build: coordinate outside [-2^17, 2^17) (or NaN point) or batch index outside [0, 1023)");
 
@@ -643,7 +656,7 @@ static int coords_build_common(egn_ctx *ctx, const BuildSource &src, int64_t n64
     ba.n[L] = py.n[L];
   }
   EGN_LAUNCH(ctx, "coords_batch_offsets", (double)P * (B + 1) * 4, 0, s,
-             k_batch_offsets<<<(int)div_up((int64_t)P * (B + 1), 128), 128, 0, s>>>(ba, B));
+             k_batch_offsets<<<(int)div_up((int64_t)P * (B + 1) * 32, 128), 128, 0, s>>>(ba, B));
 
   // kernel-map build: algorithmic bytes N*8 (keys) + N*27*4 (table) per level
   const int T = P - 1;
@@ -787,6 +800,12 @@ __global__ void k_quant_pack_batch(const float *__restrict__ pts, int n, const i
     }
     vals[i] = (uint32_t)i;
   }
+  // the first-point offsets must partition [0, n): start at 0, end at n, never decrease (checked once, by block 0)
+  if (blockIdx.x == 0)
+    for (int c = threadIdx.x; c <= n_clouds; c += blockDim.x) {
+      const int o = __ldg(cloud_off + c);
+      if ((c == 0 && o != 0) || (c == n_clouds && o != n) || (c > 0 && o < __ldg(cloud_off + c - 1))) bad |= 4;
+    }
   bad = __reduce_or_sync(0xffffffffu, bad);
   if ((threadIdx.x & 31) == 0 && bad) atomicOr(&dev_counts[P + 1], bad);
   if (blockIdx.x == 0 && threadIdx.x == 0) dev_counts[P] = n_clouds;

@@ -2,19 +2,20 @@
 // (ME.SparseTensor's coordinate hash-table build, models/minkgl.py:269) and behind sparse_quantize's de-duplication
 // (datasets/quantization.py:42,83).  Replaces cub::DeviceRadixSort.
 //
-// Sizes here are 0.75 M - 5 M pairs, i.e. 90 - 600 tiles of 8192: at that size a decoupled look-back chain (onesweep) is
+// Sizes here are 0.75 M - 5 M pairs, i.e. 180 - 1200 tiles of 4096: at that size a decoupled look-back chain (onesweep) is
 // one serial hop per tile, and a histogram + scan + scatter triple is three launches per digit.  This sort needs ONE
 // launch per 8-bit digit and no spinning:
 //   * the digit counts of every (tile, digit) of pass p+1 are accumulated BY PASS p while it scatters: an element that
-//     lands at output position q belongs to tile q / 8192 of the next pass, so the scattering warp adds its elements to
-//     hist[p+1][q / 8192][next digit] (integer atomics, aggregated over equal (tile, digit) pairs inside the warp with
+//     lands at output position q belongs to tile q / 4096 of the next pass, so the scattering warp adds its elements to
+//     hist[p+1][q / 4096][next digit] (integer atomics, aggregated over equal (tile, digit) pairs inside the warp with
 //     __match_any_sync: order-independent, deterministic).  Pass 0's counts come from a counting kernel.  A second, 16x
 //     coarser count matrix ("super-tiles") keeps the prefix walk short.
 //   * a pass CTA first turns the count matrices into its 256 output bases (digit total before it + same-digit elements of
-//     earlier tiles: <= n_super + 15 coalesced loads per thread, no waiting on other CTAs), then ranks its 8192 elements
-//     stably (a warp owns 512 consecutive elements and ranks them in order with __match_any_sync; per-(digit, warp)
+//     earlier tiles: <= n_super + 15 coalesced loads per thread, no waiting on other CTAs), then ranks its 4096 elements
+//     stably (a warp owns 256 consecutive elements and ranks them in order with __match_any_sync; per-(digit, warp)
 //     counters are scanned digit-major), stages the tile in digit order in shared memory and writes it out in runs
 //     (consecutive lanes -> consecutive addresses).
+//   * a digit position whose value is the same for all keys (known from the count matrix) costs a tile copy, not a pass.
 // Stable, deterministic, no co-residency assumption (safe under concurrent streams), 24 bytes of traffic per pair and pass.
 #include "ctx.cuh"
 
@@ -24,8 +25,8 @@ namespace {
 
 constexpr int kSortThreads = 512;
 constexpr int kSortWarps = kSortThreads / 32;       // 16
-constexpr int kSortItems = 16;                      // per thread
-constexpr int kSortTile = kSortThreads * kSortItems;   // 8192
+constexpr int kSortItems = 8;                       // per thread: 64 registers, two CTAs per SM
+constexpr int kSortTile = kSortThreads * kSortItems;   // 4096
 constexpr int kSortSuper = 16;                      // tiles per super-tile
 
 // pass-0 counts: hist_tiles[tile][digit], hist_super[tile / 16][digit]
@@ -37,12 +38,16 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_count(const uint64_t *__r
   __syncthreads();
   const int base = tile * kSortTile;
   const int lane = threadIdx.x & 31;
-#pragma unroll 4
-  for (int i = threadIdx.x; i < kSortTile; i += kSortThreads) {      // warp-uniform trip count
-    const int e = base + i;
-    const uint32_t d = e < n ? (uint32_t)((keys[e] >> shift) & 255ull) : 256u;
-    const uint32_t peers = __match_any_sync(0xffffffffu, d);        // one shared-memory atomic per distinct digit of the warp
-    if (d < 256u && lane == __ffs(peers) - 1) atomicAdd(&cnt[d], __popc(peers));
+  uint32_t d[kSortItems];
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {                           // all loads first: one memory latency per tile
+    const int e = base + r * kSortThreads + threadIdx.x;
+    d[r] = e < n ? (uint32_t)((keys[e] >> shift) & 255ull) : 256u;
+  }
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    const uint32_t peers = __match_any_sync(0xffffffffu, d[r]);    // one shared-memory atomic per distinct digit of the warp
+    if (d[r] < 256u && lane == __ffs(peers) - 1) atomicAdd(&cnt[d[r]], __popc(peers));
   }
   __syncthreads();
   if (threadIdx.x < 256) {
@@ -54,7 +59,7 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_count(const uint64_t *__r
   }
 }
 
-__global__ void __launch_bounds__(kSortThreads) k_sort_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
+__global__ void __launch_bounds__(kSortThreads, 2) k_sort_pass(const uint64_t *__restrict__ kin, const uint32_t *__restrict__ vin,
                                                             uint64_t *__restrict__ kout, uint32_t *__restrict__ vout, int n, int shift,
                                                             const int *__restrict__ hist_tiles, const int *__restrict__ hist_super,
                                                             int n_super, int *__restrict__ next_tiles, int *__restrict__ next_super,
@@ -107,7 +112,38 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_pass(const uint64_t *__re
   }
   __syncthreads();
 
-  // ---- 2. stable rank inside the tile: warp w owns elements [w * 512, (w + 1) * 512), visited in order ----
+  // ---- 1b. a digit that is the same for ALL n keys (high bits of small coordinates / batch indices): the pass is the identity
+  //          permutation - copy the tile, count its next digits, done (a fraction of the cost of a real pass) ----
+  if (__syncthreads_or(tid < 256 && total == n)) {
+    int *hcnt = (int *)cnt;                               // [256] next-digit counts of this tile
+    if (tid < 256) hcnt[tid] = 0;
+    __syncthreads();
+    const int base = tile * kSortTile;
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+      const int e = base + r * kSortThreads + tid;
+      const bool ok = e < n;
+      uint64_t k = 0;
+      if (ok) {
+        k = kin[e];
+        kout[e] = k;
+        vout[e] = vin[e];
+      }
+      if (next_shift >= 0) {
+        const uint32_t d2 = ok ? (uint32_t)((k >> next_shift) & 255ull) : 256u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, d2);
+        if (ok && lane == __ffs(peers) - 1) atomicAdd(&hcnt[d2], __popc(peers));
+      }
+    }
+    __syncthreads();
+    if (next_shift >= 0 && tid < 256 && hcnt[tid]) {
+      next_tiles[tile * 256 + tid] = hcnt[tid];
+      atomicAdd(next_super + (tile / kSortSuper) * 256 + tid, hcnt[tid]);
+    }
+    return;
+  }
+
+  // ---- 2. stable rank inside the tile: warp w owns elements [w * 256, (w + 1) * 256), visited in order ----
   uint64_t key[kSortItems];
   uint32_t val[kSortItems];
   uint16_t rank[kSortItems];

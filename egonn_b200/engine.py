@@ -233,6 +233,14 @@ class Engine:
 _retrieval_engines = {}
 
 
+def _stream_key(device):
+    """(device index, current CUDA stream, host thread): an ``egn_ctx`` holds single-stream scratch, see quantization._engine."""
+    import threading
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    return (idx, torch.cuda.current_stream(idx).cuda_stream, threading.get_ident())
+
+
 def knn_global(query: torch.Tensor, map_embeddings: torch.Tensor, k: int):
     """Nearest neighbours of every query descriptor in the map set by Euclidean distance (eval/evaluate.py:173-176).
     Returns (idx (Q,k) int64 map rows, ascending distance; dist (Q,k) f32).  CUDA tensors only."""
@@ -241,10 +249,7 @@ def knn_global(query: torch.Tensor, map_embeddings: torch.Tensor, k: int):
     q = query.detach().to(torch.float32).contiguous()
     m = map_embeddings.detach().to(torch.float32).contiguous()
     assert q.dim() == 2 and m.dim() == 2 and q.shape[1] == m.shape[1]
-    key = q.device.index or 0
-    if key not in _retrieval_engines:
-        _retrieval_engines[key] = Engine(q.device)
-    eng = _retrieval_engines[key]
+    eng = _shared_engine(q.device)
     idx = torch.empty((q.shape[0], k), dtype=torch.int32, device=q.device)
     dist = torch.empty((q.shape[0], m.shape[0]), dtype=torch.float32, device=q.device)
     with torch.cuda.device(q.device):
@@ -254,9 +259,9 @@ def knn_global(query: torch.Tensor, map_embeddings: torch.Tensor, k: int):
 
 
 def _shared_engine(device) -> "Engine":
-    key = torch.device(device).index or 0
+    key = _stream_key(device)
     if key not in _retrieval_engines:
-        _retrieval_engines[key] = Engine(torch.device("cuda", key))
+        _retrieval_engines[key] = Engine(torch.device("cuda", key[0]))
     return _retrieval_engines[key]
 
 

@@ -237,12 +237,16 @@ class _Utils:
                         return_inverse=False, return_maps_only=False, quantization_size=None, device="cpu"):
         assert features is None and labels is None and not return_inverse and not return_maps_only, \
             "only the (coordinates, return_index, quantization_size) form used by datasets/quantization.py is supported"
-        c = torch.as_tensor(coordinates)
+        c = torch.as_tensor(coordinates).float()
         if isinstance(quantization_size, (list, tuple, np.ndarray, torch.Tensor)):
-            step = [float(v) for v in quantization_size]
+            # per-axis steps: ME divides the (N,3) coordinates by the step vector (one f32 divide per element) and floors;
+            # egn_quantize's cartesian mode divides all axes by step[0], so the divide is done here, the floor there
+            q = torch.as_tensor([float(v) for v in quantization_size], dtype=torch.float32, device=c.device)
+            assert q.numel() == c.shape[1], "one quantisation step per coordinate axis"
+            c, step = c / q, 1.0
         else:
             step = 1.0 if quantization_size is None else float(quantization_size)
-        coords, ndx = _q._quantize_on_gpu(c.float(), step, polar=False)
+        coords, ndx = _q._quantize_on_gpu(c, step, polar=False)
         return (coords, ndx) if return_index else coords
 
     batched_coordinates = staticmethod(_q.batched_coordinates)

@@ -9,22 +9,34 @@ from __future__ import annotations
 from abc import ABC, abstractmethod
 from typing import List
 
+import threading
+
 import numpy as np
 import torch
 
 _engines = {}
+_engines_lock = threading.Lock()
 
 
 def _engine(device):
+    """One engine context per (device, CUDA stream, host thread): an ``egn_ctx`` holds single-stream scratch (arena, device
+    counters, pinned counts), so calls from two streams or two threads must not share one."""
     from .engine import Engine
-    key = torch.device(device).index or 0
-    if key not in _engines:
-        _engines[key] = Engine(torch.device("cuda", key))
-    return _engines[key]
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    key = (idx, torch.cuda.current_stream(idx).cuda_stream, threading.get_ident())
+    with _engines_lock:
+        eng = _engines.get(key)
+        if eng is None:
+            eng = _engines[key] = Engine(torch.device("cuda", idx))
+    return eng
 
 
 def _quantize_on_gpu(pc: torch.Tensor, step, polar: bool):
     assert pc.shape[1] == 3
+    if not torch.cuda.is_available():
+        raise RuntimeError("egonn_b200 quantises on the GPU and has no CPU path: no CUDA device is visible in this process "
+                           "(inside a forked DataLoader worker, quantise in the main process or start workers with 'spawn')")
     src = pc.device
     dev = pc.device if pc.is_cuda else torch.device("cuda", torch.cuda.current_device())
     coords, ndx = _engine(dev).quantize(pc.to(dev), step, polar)
