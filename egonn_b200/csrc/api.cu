@@ -137,7 +137,6 @@ int egn_ctx_destroy(egn_ctx *ctx) {
   ctx->feats.release();
   ctx->prof.drain();
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
-  if (ctx->splitk_buf) cudaFree(ctx->splitk_buf);
   if (ctx->aux) cudaStreamDestroy(ctx->aux);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);

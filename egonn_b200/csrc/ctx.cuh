@@ -96,8 +96,7 @@ struct egn_ctx {
   void *trace = nullptr;            // debug timeline buffer for k_sconv_tc (EGN_TRACE=1 allocates 64*8 int64)
   int nsplit_max = 74;              // N-split 128-channel convolutions up to this many row tiles (EGN_NSPLIT_MAX)
   bool ksplit = false;              // K-split of small 128-channel levels (EGN_KSPLIT=1)
-  void *splitk_buf = nullptr;       // raw partial tiles of K-split convolutions (small levels only)
-  size_t splitk_cap = 0;
+  bool in_forward = false;          // inside egn_forward: temporaries come from the planned feature arena
 };
 
 // opt a kernel in to `bytes` of dynamic shared memory once per context (the current device must be ctx->device)

@@ -79,9 +79,12 @@ size_t plan_floats(const Pyramid &py, const egn_net &net) {
   for (int L = 1; L <= net.n_levels; ++L) {
     const size_t n = py.n[L] + 1;                          // + the zero row of pre-split maps
     f += n * net.down[L].cout + 3 * n * net.conv2[L].cout + (net.res[L].cin ? n * net.res[L].cout : 0) + 1024;
+    f += (size_t)net.n_extra[L] * (3 * n * net.conv2[L].cout + ((size_t)kNumSMs * 8 + 2 * (size_t)py.n_batches) * net.conv2[L].cout + 256);   // blocks 1..
     f += 2 * n * net.conv2[L].cout;                        // fp32 copies for consumers that cannot read a pre-split map (rare)
     f += ((size_t)kNumSMs * 8 + 2 * (size_t)py.n_batches) * net.conv2[L].cout + 128;   // pooling partials (<= 8 CTAs per SM) + gates
   }
+  for (int L = 1; L <= net.n_levels; ++L)                   // K-split partial tiles (3 splits, levels of <= 37 row tiles, EGN_KSPLIT=1)
+    if (py.n[L] <= 37 * 128) f += 2 * 3 * (size_t)py.n[L] * net.conv2[L].cout + 64;
   f += head_floats(py, net.global_head) + head_floats(py, net.local_head);
   if (net.global_head.n_levels) {
     const size_t n = py.n[net.global_head.levels[0]];
@@ -131,6 +134,11 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
             "forward: local outputs need a local head and all three buffers");
 
   EGN_TRY(ctx->feats.reserve(plan_floats(py, *net) * 4, s));
+  struct InForward {                                        // run_conv_tc takes its K-split temporaries from the feature arena
+    egn_ctx *c;
+    explicit InForward(egn_ctx *c_) : c(c_) { c->in_forward = true; }
+    ~InForward() { c->in_forward = false; }
+  } in_forward_guard(ctx);
   Fwd F{ctx, net, weights, s};
   Taps &tp = ctx->taps;
   tp = Taps();
@@ -200,7 +208,10 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
     // pre-split where the producer can write it (a tensor-core convolution / the fused residual pass) and the main consumer gathers it
     d.split = F.tc_ok(net->down[L], 2, 0) && F.want_split(net->conv1[L], 3, 0);
     t1.split = F.tc_ok(net->conv1[L], 3, 0) && F.want_split(net->conv2[L], 3, 0);
-    xo.split = L < net->n_levels && F.want_split(net->down[L + 1], 2, 0);
+    const int n_extra = net->n_extra[L];
+    EGN_CHECK(n_extra >= 0 && n_extra <= EGN_MAX_EXTRA_BLOCKS, EGN_ERR_INVALID, "forward: %d extra blocks at level %d", n_extra, L);
+    // the block output feeds the next block's 3x3x3 convolution (layers[L] > 1) or the next level's stride-2 convolution
+    xo.split = n_extra > 0 ? F.want_split(net->xconv1[L][0], 3, 0) : (L < net->n_levels && F.want_split(net->down[L + 1], 2, 0));
     EGN_TRY(F.layer(net->down[L], L - 1, 2, 0, cur, 1, 0, d));              // convs[L] + bn[L] + relu
     EGN_TRY(F.layer(net->conv1[L], L, 3, 0, d, 1, 0, t1));                  // conv1 + norm1 + relu
     EGN_TRY(F.layer(net->conv2[L], L, 3, 0, t1, 0, 0, t2));                 // conv2 + norm2
@@ -223,6 +234,27 @@ int forward(egn_ctx *ctx, const egn_net *net, const float *weights, const float 
       gate = g;
     }
     EGN_TRY(run_eca_apply(ctx, L, c, t2.p, res.p, gate, 1, res.split, xo.split, xo.p, s));   // out = relu(eca(out) + residual)
+    for (int j = 0; j < n_extra; ++j) {                                     // blocks 1.. : same channels, identity residual
+      const egn_layer &c1 = net->xconv1[L][j], &c2 = net->xconv2[L][j];
+      EGN_CHECK(c1.cin == c && c1.cout == c && c2.cin == c && c2.cout == c, EGN_ERR_INVALID, "extra block %d of level %d must keep %d channels", j + 1, L, c);
+      Map u1, u2, xn;
+      u1.p = F.alloc_map(n, c); u2.p = F.alloc_map(n, c); xn.p = F.alloc_map(n, c);
+      EGN_CHECK(u1.p && u2.p && xn.p, EGN_ERR_STATE, "feature arena exhausted (level %d block %d)", L, j + 1);
+      u1.split = F.tc_ok(c1, 3, 0) && F.want_split(c2, 3, 0);
+      xn.split = j + 1 < n_extra ? F.want_split(net->xconv1[L][j + 1], 3, 0) : (L < net->n_levels && F.want_split(net->down[L + 1], 2, 0));
+      EGN_TRY(F.layer(c1, L, 3, 0, xo, 1, 0, u1));
+      EGN_TRY(F.layer(c2, L, 3, 0, u1, 0, 0, u2));
+      const float *g2 = nullptr;
+      if (net->xeca_k[L][j] > 0) {
+        const int slices = pool_slices_for(ctx, L);
+        float *part = F.alloc((size_t)py.n_batches * slices * c), *g = F.alloc((size_t)py.n_batches * c);
+        EGN_CHECK(part && g, EGN_ERR_STATE, "feature arena exhausted (eca)");
+        EGN_TRY(run_eca_gate(ctx, L, c, u2.p, F.W(net->xeca_w[L][j]), net->xeca_k[L][j], part, slices, g, s));
+        g2 = g;
+      }
+      EGN_TRY(run_eca_apply(ctx, L, c, u2.p, xo.p, g2, 1, xo.split, xn.split, xn.p, s));
+      xo = xn;
+    }
     x[L] = xo;
     cur = xo;
     tp.down[L] = d.p; tp.c_down[L] = net->down[L].cout; tp.down_split[L] = d.split;

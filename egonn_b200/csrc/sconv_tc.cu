@@ -100,14 +100,15 @@ int run_conv_tc(egn_ctx *ctx, int level_in, int ksize, int transposed, int cin, 
       float *part = nullptr;
       if (splits > 1) {
         const size_t bytes_part = (size_t)splits * a.n_out * cout * 4;
-        if (ctx->splitk_cap < bytes_part) {
-          EGN_CUDA(cudaStreamSynchronize(s));
-          if (ctx->splitk_buf) EGN_CUDA(cudaFree(ctx->splitk_buf));
-          ctx->splitk_buf = nullptr; ctx->splitk_cap = 0;
-          EGN_CUDA(cudaMalloc((void **)&ctx->splitk_buf, bytes_part * 2));
-          ctx->splitk_cap = bytes_part * 2;
+        // raw partial tiles: from the feature arena inside a forward (planned by forward.cu), from the scratch arena for a
+        // single-operator call (dead sort buffers; reuse on the same stream is stream-ordered) - no cudaMalloc on this path
+        if (ctx->in_forward) {
+          part = (float *)ctx->feats.take(bytes_part);
+        } else {
+          EGN_TRY(ctx->scratch.reserve(bytes_part + 4096, s));
+          part = (float *)ctx->scratch.take(bytes_part);
         }
-        part = (float *)ctx->splitk_buf;
+        EGN_CHECK(part != nullptr, EGN_ERR_STATE, "arena exhausted (K-split partial tiles)");
         b.out = part; b.scale = nullptr; b.shift = nullptr; b.relu = 0; b.ksplit = splits;
       }
       EGN_TRY(launch_conv_ts(ctx, K, 128, tiles <= 37 ? 32 : 64, b, name, bytes, flops, s));

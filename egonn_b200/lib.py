@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libegonn_b200.so")
 EGN_MAX_LEVELS = 8
 EGN_PYR_LEVELS = 10
 EGN_MAX_HEAD_LEVELS = 4
+EGN_MAX_EXTRA_BLOCKS = 3
 
 
 class EgnError(RuntimeError):
@@ -40,7 +41,10 @@ class Net(C.Structure):
                 ("pool_method", C.c_int32), ("gem_p", C.c_float), ("gem_eps", C.c_float),
                 ("desc_mlp", Layer * 2), ("kp_mlp", Layer * 2), ("sigma_mlp", Layer * 2),
                 ("polar", C.c_int32), ("quant_step", C.c_float * 3), ("ignore_keypoint_regressor", C.c_int32),
-                ("kpsig_mlp", Layer * 2)]
+                ("kpsig_mlp", Layer * 2),
+                ("n_extra", C.c_int32 * EGN_MAX_LEVELS), ("xconv1", (Layer * EGN_MAX_EXTRA_BLOCKS) * EGN_MAX_LEVELS),
+                ("xconv2", (Layer * EGN_MAX_EXTRA_BLOCKS) * EGN_MAX_LEVELS), ("xeca_k", (C.c_int32 * EGN_MAX_EXTRA_BLOCKS) * EGN_MAX_LEVELS),
+                ("xeca_w", (C.c_int64 * EGN_MAX_EXTRA_BLOCKS) * EGN_MAX_LEVELS)]
 
 
 class ProfileEntry(C.Structure):

@@ -146,7 +146,7 @@ class MinkTrunk(nn.Module):
         self.in_channels, self.planes = in_channels, planes
         self.layers = [1] * len(planes) if layers is None else layers
         assert len(self.layers) == len(planes) and min_out_level <= len(planes)
-        assert all(n == 1 for n in self.layers), "the CUDA engine schedules one block per level (as every shipped config does)"
+        assert all(1 <= n <= 4 for n in self.layers), "the CUDA engine schedules 1..4 blocks per level"
         self.conv0_kernel_size, self.block, self.min_out_level = conv0_kernel_size, block, min_out_level
         self.num_bottom_up = len(planes)
         self.init_dim = planes[0]
@@ -399,7 +399,7 @@ class MinkFPN(nn.Module):
                  layers=(1, 1, 1), planes=(32, 64, 64)):
         super().__init__()
         assert len(layers) == len(planes) and 1 <= len(layers) and 0 <= num_top_down <= len(layers)
-        assert all(n == 1 for n in layers), "the CUDA engine schedules one block per level"
+        assert all(1 <= n <= 4 for n in layers), "the CUDA engine schedules 1..4 blocks per level"
         self.num_bottom_up, self.num_top_down = len(layers), num_top_down
         self.conv0_kernel_size, self.block, self.layers, self.planes = conv0_kernel_size, block, layers, planes
         self.lateral_dim, self.init_dim = out_channels, planes[0]
@@ -408,10 +408,10 @@ class MinkFPN(nn.Module):
         self.inplanes = planes[0]
         conv0 = ME.MinkowskiConvolution(in_channels, self.inplanes, kernel_size=conv0_kernel_size, dimension=3)
         bn0 = ME.MinkowskiBatchNorm(self.inplanes)
-        for plane in planes:
+        for plane, n_blocks in zip(planes, layers):
             self.convs.append(ME.MinkowskiConvolution(self.inplanes, self.inplanes, kernel_size=2, stride=2, dimension=3))
             self.bn.append(ME.MinkowskiBatchNorm(self.inplanes))
-            self.blocks.append(self._make_layer(block, plane))
+            self.blocks.append(self._make_layer(block, plane, n_blocks))
         for i in range(num_top_down):
             self.conv1x1.append(ME.MinkowskiConvolution(planes[-1 - i], out_channels, kernel_size=1, stride=1, dimension=3))
             self.tconvs.append(ME.MinkowskiConvolutionTranspose(out_channels, out_channels, kernel_size=2, stride=2, dimension=3))
@@ -426,15 +426,16 @@ class MinkFPN(nn.Module):
                 nn.init.constant_(m.bn.weight, 1)
                 nn.init.constant_(m.bn.bias, 0)
 
-    def _make_layer(self, block, planes):
+    def _make_layer(self, block, planes, blocks=1):                   # models/resnet.py:81-97
         downsample = None
         if self.inplanes != planes * block.expansion:
             downsample = nn.Sequential(
                 ME.MinkowskiConvolution(self.inplanes, planes * block.expansion, kernel_size=1, stride=1, dimension=3),
                 ME.MinkowskiBatchNorm(planes * block.expansion))
-        layer = nn.Sequential(block(self.inplanes, planes, stride=1, dilation=1, downsample=downsample, dimension=3))
+        seq = [block(self.inplanes, planes, stride=1, dilation=1, downsample=downsample, dimension=3)]
         self.inplanes = planes * block.expansion
-        return layer
+        seq += [block(self.inplanes, planes, stride=1, dilation=1, dimension=3) for _ in range(1, blocks)]
+        return nn.Sequential(*seq)
 
     def forward(self, x):                                             # layer-wise operator walk (models/minkfpn.py:65-93)
         maps = []

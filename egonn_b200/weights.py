@@ -118,6 +118,22 @@ def _linear(blob, sd, prefix, pad_in: int = 0, pad_out: int = 0) -> L.Layer:
     return lay
 
 
+def _extra_blocks(blob, net, sd, lv: int, prefix: str, bn_eps: float):
+    """Blocks 1.. of level ``lv`` (``{prefix}.{j}``, j >= 1): same channels in and out, identity residual."""
+    j = 1
+    while f"{prefix}.{j}.conv1.kernel" in sd:
+        assert j <= L.EGN_MAX_EXTRA_BLOCKS, f"at most {L.EGN_MAX_EXTRA_BLOCKS + 1} blocks per level"
+        p = f"{prefix}.{j}"
+        assert p + ".downsample.0.kernel" not in sd, "only the first block of a level may change the channel count"
+        net.xconv1[lv][j - 1] = _conv(blob, sd[p + ".conv1.kernel"], _bn_fold(sd, p + ".norm1.bn", bn_eps))
+        net.xconv2[lv][j - 1] = _conv(blob, sd[p + ".conv2.kernel"], _bn_fold(sd, p + ".norm2.bn", bn_eps))
+        if p + ".eca.conv.weight" in sd:
+            w = sd[p + ".eca.conv.weight"].reshape(-1)
+            net.xeca_k[lv][j - 1], net.xeca_w[lv][j - 1] = w.numel(), blob.add(w)
+        j += 1
+    net.n_extra[lv] = j - 1
+
+
 def _head(blob, sd, prefix, levels, out_channels) -> L.Head:
     h = L.Head()
     h.n_levels = len(levels)
@@ -146,7 +162,7 @@ def pack_egonn(sd: Dict[str, torch.Tensor], quantizer_desc: dict, global_levels=
     for lv in range(1, n_levels + 1):
         net.down[lv] = _conv(blob, sd[f"trunk.convs.{lv}.kernel"], _bn_fold(sd, f"trunk.bn.{lv}.bn", bn_eps))
         p = f"trunk.blocks.{lv}.0"
-        assert f"trunk.blocks.{lv}.1.conv1.kernel" not in sd, "more than one block per level is not supported yet"
+        _extra_blocks(blob, net, sd, lv, f"trunk.blocks.{lv}", bn_eps)
         net.conv1[lv] = _conv(blob, sd[p + ".conv1.kernel"], _bn_fold(sd, p + ".norm1.bn", bn_eps))
         net.conv2[lv] = _conv(blob, sd[p + ".conv2.kernel"], _bn_fold(sd, p + ".norm2.bn", bn_eps))
         if p + ".downsample.0.kernel" in sd:
@@ -222,7 +238,7 @@ def pack_minkfpn(sd: Dict[str, torch.Tensor], quantizer_desc: dict, num_top_down
         i = lv - 1
         net.down[lv] = _conv(blob, sd[f"{b}.convs.{i}.kernel"], _bn_fold(sd, f"{b}.bn.{i}.bn", bn_eps))
         p = f"{b}.blocks.{i}.0"
-        assert f"{b}.blocks.{i}.1.conv1.kernel" not in sd, "more than one block per level is not supported yet"
+        _extra_blocks(blob, net, sd, lv, f"{b}.blocks.{i}", bn_eps)
         net.conv1[lv] = _conv(blob, sd[p + ".conv1.kernel"], _bn_fold(sd, p + ".norm1.bn", bn_eps))
         net.conv2[lv] = _conv(blob, sd[p + ".conv2.kernel"], _bn_fold(sd, p + ".norm2.bn", bn_eps))
         if p + ".downsample.0.kernel" in sd:

@@ -43,6 +43,7 @@ extern "C" {
 #define EGN_MAX_LEVELS 8   /* network levels 0..7 (tensor stride 1..128) */
 #define EGN_PYR_LEVELS 10  /* coordinate pyramid levels kept per context: 0..9 */
 #define EGN_MAX_HEAD_LEVELS 4
+#define EGN_MAX_EXTRA_BLOCKS 3 /* residual blocks per level beyond the first (layers[L] <= 4) */
 
 typedef struct egn_ctx egn_ctx;
 typedef void *egn_stream_t; /* cudaStream_t */
@@ -154,6 +155,14 @@ typedef struct {
    * local map, so their first Linear layers run as ONE 64 -> 32+32 layer and their second layers as ONE block-diagonal
    * (32+32) -> 3+1 layer; identical arithmetic per output (the extra weights are exact zeros).  models/minkgl.py:175-204 */
   egn_layer kpsig_mlp[2];
+  /* Blocks 1.. of a level when layers[L] > 1 (MinkTrunk._make_layer models/minkgl.py:121-134 / ResNetBase._make_layer
+   * models/resnet.py:81-97: the blocks after the first keep the channel count and have an identity residual).  Block j+1
+   * of level L: xconv1[L][j] + norm1 + ReLU, xconv2[L][j] + norm2, ECA gate xeca_*[L][j] (k == 0: plain BasicBlock). */
+  int32_t n_extra[EGN_MAX_LEVELS];
+  egn_layer xconv1[EGN_MAX_LEVELS][EGN_MAX_EXTRA_BLOCKS];
+  egn_layer xconv2[EGN_MAX_LEVELS][EGN_MAX_EXTRA_BLOCKS];
+  int32_t xeca_k[EGN_MAX_LEVELS][EGN_MAX_EXTRA_BLOCKS];
+  int64_t xeca_w[EGN_MAX_LEVELS][EGN_MAX_EXTRA_BLOCKS];
 } egn_net;
 
 /* Keep the weight blob resident in L2 across forwards: reserves a persisting-L2 carve-out

@@ -71,7 +71,11 @@ def trunk(sd, cm, feats, n_levels, n_batches, acc64=False, keep=None):
         x = torch.relu(_bn(sd, f"trunk.bn.{i}", x))
         if keep is not None:
             keep[f"down{i}"] = x
-        x = eca_basic_block(sd, f"trunk.blocks.{i}.0", cm, x, stride, n_batches, acc64=acc64)
+        j = 0
+        while f"trunk.blocks.{i}.{j}.conv1.kernel" in sd:              # layers[i] blocks per level (models/minkgl.py:121-134)
+            x = eca_basic_block(sd, f"trunk.blocks.{i}.{j}", cm, x, stride, n_batches, acc64=acc64,
+                                eca=f"trunk.blocks.{i}.{j}.eca.conv.weight" in sd)
+            j += 1
         y[i] = x
     return y
 
@@ -214,8 +218,11 @@ def forward_minkloc(sd: Dict[str, torch.Tensor], coords, feats: torch.Tensor, nu
     for ndx in range(n_levels):
         x, stride = me_ops.convolution(cm, x, stride, sd[f"{b}.convs.{ndx}.kernel"], 2, stride=2, acc64=acc64)
         x = torch.relu(_bn(sd, f"{b}.bn.{ndx}", x))
-        has_eca = f"{b}.blocks.{ndx}.0.eca.conv.weight" in sd
-        x = eca_basic_block(sd, f"{b}.blocks.{ndx}.0", cm, x, stride, nb, acc64=acc64, eca=has_eca)
+        j = 0
+        while f"{b}.blocks.{ndx}.{j}.conv1.kernel" in sd:               # layers[ndx] blocks per level (models/resnet.py:81-97)
+            x = eca_basic_block(sd, f"{b}.blocks.{ndx}.{j}", cm, x, stride, nb, acc64=acc64,
+                                eca=f"{b}.blocks.{ndx}.{j}.eca.conv.weight" in sd)
+            j += 1
         if n_levels - 1 - num_top_down <= ndx < n_levels - 1:
             maps.append((stride, x))
     x, _ = me_ops.convolution(cm, x, stride, sd[f"{b}.conv1x1.0.kernel"], 1, acc64=acc64)
