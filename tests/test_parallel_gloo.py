@@ -49,3 +49,26 @@ def test_allgather_global_descriptors_world2(tmp_path):
     full = torch.load(out)
     expect = torch.stack([i + torch.arange(256) / 1000.0 for i in range(5)])
     assert torch.equal(full, expect)
+
+
+def test_sharded_batch_partition_and_imbalance():
+    """Host logic of the strong-scaling path (bench.py --strong): the rank's share, its batched coordinates and the
+    load imbalance, on CPU tensors (no forward)."""
+    from egonn_b200.parallel import ShardedBatch
+    sizes = [900, 100, 500, 400, 300, 800]
+    clouds = [torch.zeros((n, 3), dtype=torch.int32) + i for i, n in enumerate(sizes)]
+
+    def batched(cs):
+        return torch.cat([torch.cat([torch.full((c.shape[0], 1), b, dtype=torch.int32), c], dim=1) for b, c in enumerate(cs)])
+
+    shares = [ShardedBatch(clouds, batched, r, 3) for r in range(3)]
+    assert sorted(i for sb in shares for i in sb.mine) == list(range(6))
+    assert all(sb.parts == shares[0].parts and sb.loads == shares[0].loads for sb in shares)
+    for sb in shares:
+        assert sb.coords.shape == (sum(sizes[i] for i in sb.mine), 4)
+        assert sb.coords[:, 0].unique().tolist() == list(range(len(sb.mine)))          # batch indices restart at 0 on every rank
+        first = sb.coords[sb.coords[:, 0] == 0][0, 1].item()
+        assert first == sb.mine[0]                                                      # share keeps ascending original order
+    assert 1.0 <= shares[0].imbalance <= 1.1
+    empty = ShardedBatch(clouds[:2], batched, 3, 4)                                     # more ranks than clouds
+    assert empty.mine == [] and empty.coords is None
