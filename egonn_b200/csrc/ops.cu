@@ -503,20 +503,34 @@ __global__ void k_eca_apply(const float4 *__restrict__ t, const float4 *__restri
                             const uint64_t *__restrict__ keys, int batch_shift, int n, int c4, int relu, int res_split, int out_split,
                             float4 *__restrict__ out) {
   const int64_t total = (int64_t)n * c4;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / c4), q = (int)(i % c4);
-    float4 v = t[i];
-    if (gate) {
-      const int b = (int)(keys[r] >> batch_shift);
-      const float4 g = *(const float4 *)(gate + ((size_t)b * c4 + q) * 4);
-      v.x *= g.x; v.y *= g.y; v.z *= g.z; v.w *= g.w;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  constexpr int U = 4;                                      // four 16-byte elements in flight per thread (pure streaming pass)
+  for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < total; i0 += U * stride) {
+    float4 v[U], rr[U];
+    uint64_t key[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i < total) {
+        v[u] = t[i];
+        if (gate) key[u] = keys[(int)(i / c4)];
+        if (res) rr[u] = res_split ? presplit_unpack(((const uint4 *)res)[i]) : res[i];
+      }
     }
-    if (res) {
-      const float4 rr = res_split ? presplit_unpack(((const uint4 *)res)[i]) : res[i];
-      v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t i = i0 + u * stride;
+      if (i >= total) continue;
+      float4 x = v[u];
+      if (gate) {
+        const int b = (int)(key[u] >> batch_shift), q = (int)(i % c4);
+        const float4 g = *(const float4 *)(gate + ((size_t)b * c4 + q) * 4);
+        x.x *= g.x; x.y *= g.y; x.z *= g.z; x.w *= g.w;
+      }
+      if (res) { x.x += rr[u].x; x.y += rr[u].y; x.z += rr[u].z; x.w += rr[u].w; }
+      if (relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+      if (out_split) ((uint4 *)out)[i] = presplit_pack(x); else out[i] = x;
     }
-    if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-    if (out_split) ((uint4 *)out)[i] = presplit_pack(v); else out[i] = v;
   }
   if (out_split && blockIdx.x == 0 && (int)threadIdx.x < c4) out[total + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
