@@ -8,7 +8,7 @@ A step = one pass of the hot path over one batch of synthetic clouds (default: B
 KITTI-64-beam-shaped clouds, 0.10 m voxels, per GPU: weak scaling).
   value : clouds/s with the voxelised batches already resident in HBM (egn_coords_build + egn_forward + top-256
           keypoint selection); EXACTLY K steps between two synchronisations, device time by CUDA events around the
-          region, K steps round-robin over --streams (default 3) engine contexts, max over ranks.  Cold inputs: the
+          region, K steps over --streams (default 4) engine contexts, each fed by its own host thread, max over ranks.  Cold inputs: the
           steps rotate through enough DISTINCT voxelised batches (translated copies of the workload) that the inputs
           in rotation exceed the L2 (config.input_rotation); every step also writes ~1 GB of fresh activations.
           value_l2_flush is the round-1 protocol for continuity: same loop with a 256 MiB memset before every step
@@ -23,7 +23,8 @@ KITTI-64-beam-shaped clouds, 0.10 m voxels, per GPU: weak scaling).
 
 Multi-GPU (torchrun, one process per GPU): weak scaling by default (every rank extracts its own --batch clouds); the ONE
 collective of the path - the all-gather of the (clouds, 256) global descriptors - is issued through the engine's own
-NCCL communicator (egn_allgather_global, one communicator per CUDA stream) on the step's stream.  --strong runs the
+NCCL communicator (egn_allgather_global) on a dedicated communication stream behind an event of the step: a rank's
+compute streams never wait for the other ranks; the timed region ends after the last gather.  --strong runs the
 config's TOTAL batch (cfg4: 256 clouds) sharded over the ranks by egonn_b200.parallel (greedy balance by voxel count,
 original order restored after the gather); --no-gather is the ablation that drops the collective.
 """
@@ -179,7 +180,7 @@ def main():
     ap.add_argument("--config", default="cfg2", choices=list(synth.CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="clouds per GPU per step (default: the config's batch)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--streams", type=int, default=3, help="concurrent CUDA streams / engine contexts per GPU")
+    ap.add_argument("--streams", type=int, default=4, help="concurrent CUDA streams / engine contexts / host threads per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strong", action="store_true", help="strong scaling: the config's total batch sharded over the ranks (egonn_b200.parallel)")
     ap.add_argument("--no-gather", action="store_true", help="ablation: skip the all-gather of global descriptors")
@@ -214,9 +215,13 @@ def main():
     S = max(1, args.streams)
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     do_gather = world > 1 and not args.no_gather
-    # one engine-owned NCCL communicator per stream: steps on different streams never share (or reorder) a communicator
+    # the engine's own NCCL communicator on a dedicated communication stream: a step hands its global descriptors over with
+    # an event and its compute stream goes on with the next batch - it never waits for the other ranks inside the
+    # collective (every rank issues the gathers in step order, so one communicator serves all compute streams)
+    # (one communicator + side stream per compute stream / host thread: thread t runs steps t, t+S, ... on every rank, so
+    # the gathers of a communicator pair up step for step)
     comms = [parallel.Communicator(dev) for _ in range(S)] if do_gather else []
-    comm_of = {st.cuda_stream: c for st, c in zip(streams, comms)}
+    comm_streams = [torch.cuda.Stream(device=dev) for _ in range(S)] if do_gather else []
 
     # ---- device-resident voxelised batch (the `value` arm) ----
     imbalance = None
@@ -248,42 +253,68 @@ def main():
     NB = max(2, -(-int(1.25 * L2_BYTES) // in_bytes))
     shifts = [(7 * k, -5 * k, (k % 3)) for k in range(NB)]
     rot_coords = [(bcoords + torch.tensor([0, dx, dy, dz], dtype=bcoords.dtype, device=dev)).contiguous() for dx, dy, dz in shifts]
-    step_no = [0]
+    model._pack(dev)                                      # weights packed before the worker threads start
 
-    def step_device():
-        cur = torch.cuda.current_stream().cuda_stream
-        bc = rot_coords[step_no[0] % NB]
-        step_no[0] += 1
+    def step_device(i, t):
+        """Step i on compute stream t (the current stream of the calling thread)."""
+        bc = rot_coords[i % NB]
         if args.strong:
             if do_gather:
-                sb.coords = bc
-                g_all, p = parallel.run_sharded(model, sb, comm=comm_of.get(cur))
+                share = parallel.ShardedBatch.__new__(parallel.ShardedBatch)      # this step's view of the share: rotated coordinates
+                share.__dict__.update(sb.__dict__)
+                share.coords = bc
+                g_all, p = parallel.run_sharded(model, share, comm=comms[t], comm_stream=comm_streams[t])
             else:
                 p = model.forward_packed({"coords": bc, "features": feats})
         else:
             p = model.forward_packed({"coords": bc, "features": feats})
             if do_gather:
-                comm_of[cur].all_gather(p["global"], gathered[streams_index[cur]])
+                g, buf = p["global"], gathered[t]
+                parallel.on_side_stream(comm_streams[t], lambda: comms[t].all_gather(g, buf), g)
         idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK)
         return p, idx
-    streams_index = {st.cuda_stream: i for i, st in enumerate(streams)}
+
+    def run_workers(fn, n_steps):
+        """S host threads, one per compute stream: thread t issues steps t, t+S, ...  A step blocks its host thread once
+        (the row counts of egn_coords_build must reach the host); with one thread per stream the other streams keep being
+        fed meanwhile (ctypes releases the GIL inside the C ABI)."""
+        errors = []
+
+        def work(t):
+            try:
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(streams[t]):
+                    for i in range(t, n_steps, S):
+                        fn(i, t)
+            except BaseException as exc:                                          # surfaced by the main thread
+                errors.append(exc)
+
+        threads = [threading.Thread(target=work, args=(t,)) for t in range(S)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        if errors:
+            raise errors[0]
 
     def run_device(n_steps, do_flush=False):
-        """n_steps steps round-robin over S streams (one engine context each): a batch's small upper pyramid levels
-        overlap the other batch's large levels.  Inputs rotate (cold); do_flush adds the round-1 protocol's 256 MiB
-        memset before every step, INSIDE the timed region."""
+        """n_steps steps over S streams (one engine context and one host thread each): a batch's small upper pyramid
+        levels overlap the other batches' large levels.  Inputs rotate (cold); do_flush adds the round-1 protocol's
+        256 MiB memset before every step, INSIDE the timed region."""
         cur = torch.cuda.current_stream()
         start = torch.cuda.Event(enable_timing=True)
         end = torch.cuda.Event(enable_timing=True)
         start.record(cur)
         for st in streams:
             st.wait_event(start)
-        for i in range(n_steps):
-            with torch.cuda.stream(streams[i % S]):
-                if do_flush:
-                    flush.zero_()
-                step_device()
-        for st in streams:
+
+        def one(i, t):
+            if do_flush:
+                flush.zero_()
+            step_device(i, t)
+
+        run_workers(one, n_steps)
+        for st in streams + comm_streams:
             e = torch.cuda.Event()
             e.record(st)
             cur.wait_event(e)
@@ -303,7 +334,7 @@ def main():
     host_in[: n_pts * 3] = torch.from_numpy(np.concatenate(clouds, axis=0).reshape(-1))
     host_in[n_pts * 3:] = torch.from_numpy(starts).view(torch.float32)
     h2d_bytes = stage_words * 4
-    NS = max(2, S)                                        # device slots: H2D of later steps overlaps compute of earlier ones
+    NS = 2 * S                                            # two device / host slots per compute stream (= host thread)
     dev_in = [torch.empty((stage_words,), dtype=torch.float32, device=dev) for _ in range(NS)]
     dev_pts = [t[: n_pts * 3].view(n_pts, 3) for t in dev_in]
     dev_off = [t[n_pts * 3:].view(torch.int32) for t in dev_in]
@@ -311,40 +342,45 @@ def main():
     dev_out = [torch.empty((batch, per_cloud), dtype=torch.float32, device=dev) for _ in range(NS)]
     host_out = [torch.empty((batch, per_cloud), dtype=torch.float32).pin_memory() for _ in range(NS)]
     d2h_bytes = batch * per_cloud * 4
-    copy_stream = torch.cuda.Stream(device=dev)
+    copy_streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     ev_h2d = [torch.cuda.Event() for _ in range(NS)]
     ev_done = [torch.cuda.Event() for _ in range(NS)]
     for e in ev_done:
         e.record()
+    torch.cuda.synchronize()
 
-    def enqueue_h2d(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(ev_done[slot])              # the previous user of this slot has finished
+    def enqueue_h2d(slot, t):
+        with torch.cuda.stream(copy_streams[t]):
+            copy_streams[t].wait_event(ev_done[slot])          # the previous user of this slot has finished
             dev_in[slot].copy_(host_in, non_blocking=True)     # ONE host-to-device copy per step
-            ev_h2d[slot].record(copy_stream)
+            ev_h2d[slot].record(copy_streams[t])
 
-    def compute_e2e(slot):
-        with torch.cuda.stream(streams[slot % S]):
-            cur = torch.cuda.current_stream()
-            cur.wait_event(ev_h2d[slot])
-            p = model.forward_points(dev_pts[slot], dev_off[slot])
-            idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK)
-            E.pack_topk(idx, p["local_offsets"], p["keypoints"], p["descriptors"], p["global"], out=dev_out[slot])
-            host_out[slot].copy_(dev_out[slot], non_blocking=True)   # ONE device-to-host copy per step
-            if do_gather:
-                if args.strong:
-                    parallel.gather_global(p["global"], sb.parts, comm=comm_of[cur.cuda_stream])
-                else:
-                    comm_of[cur.cuda_stream].all_gather(p["global"], gathered[slot % S])
-            ev_done[slot].record(cur)
+    def step_e2e(i, t, n_steps):
+        """One end-to-end step of host thread t: ONE host-to-device copy of the raw points (on the thread's copy stream,
+        issued one step ahead into its other slot), fused quantise + pyramid, forward, top-k, pack, ONE device-to-host copy."""
+        j = i // S                                             # the thread's own step counter
+        slot = 2 * t + (j & 1)
+        if j == 0:
+            enqueue_h2d(slot, t)
+        if i + S < n_steps:
+            enqueue_h2d(2 * t + ((j + 1) & 1), t)              # next step's points travel while this step computes
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev_h2d[slot])
+        p = model.forward_points(dev_pts[slot], dev_off[slot])
+        idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK)
+        E.pack_topk(idx, p["local_offsets"], p["keypoints"], p["descriptors"], p["global"], out=dev_out[slot])
+        host_out[slot].copy_(dev_out[slot], non_blocking=True)   # ONE device-to-host copy per step
+        if do_gather:
+            g = p["global"]
+            if args.strong:
+                parallel.on_side_stream(comm_streams[t], lambda: parallel.gather_global(g, sb.parts, comm=comms[t]), g)
+            else:
+                buf = gathered[t]
+                parallel.on_side_stream(comm_streams[t], lambda: comms[t].all_gather(g, buf), g)
+        ev_done[slot].record(cur)
 
     def run_e2e(n_steps):
-        for i in range(min(NS - 1, n_steps)):
-            enqueue_h2d(i % NS)
-        for i in range(n_steps):
-            if i + NS - 1 < n_steps:
-                enqueue_h2d((i + NS - 1) % NS)
-            compute_e2e(i % NS)
+        run_workers(lambda i, t: step_e2e(i, t, n_steps), n_steps)
         torch.cuda.synchronize()
 
     def barrier():
@@ -365,9 +401,11 @@ def main():
     total_ms = run_device(K)
     barrier()
     t_wall = time.perf_counter() - t_wall0
+
+    engines = list(model._engines.values())
+    launches = (sum(e.launch_count() for e in engines) - launches0) / K + 1        # + the top-k kernel of every step (NCCL's kernel not counted)
     flush_ms = run_device(K, do_flush=True) / K         # round-1 protocol, for continuity
     barrier()
-    launches = (sum(e.launch_count() for e in engines) - launches0) / K + 1        # + the top-k kernel of every step (NCCL's kernel not counted)
     ms_step = float(total_ms / K)
     eng = model._engine
 
@@ -382,12 +420,12 @@ def main():
 
     # ---- per-kernel-class profile (separate pass so the event brackets do not perturb the timed region) ----
     with torch.cuda.stream(streams[0]):             # every rank: same stream, same number of steps (the collective stays in order)
-        step_device()
+        step_device(0, 0)
         eng = model._engine
         eng.profile(True)
-        for _ in range(min(K, 10)):
+        for j in range(min(K, 10)):
             flush.zero_()
-            step_device()
+            step_device(j + 1, 0)
         torch.cuda.synchronize()
         prof = eng.profile_read()
         eng.profile(False)
@@ -440,10 +478,10 @@ def main():
                            "input_rotation": {"distinct_batches": NB, "bytes_in_rotation": NB * in_bytes, "l2_bytes": L2_BYTES,
                                               "note": "steps rotate through translated copies of the voxelised workload: inputs in rotation > L2; "
                                                       "value_l2_flush repeats the round-1 protocol (256 MiB memset per step inside the timed region)"},
-                           "streams_per_gpu": S,
+                           "streams_per_gpu": S, "host_threads_per_gpu": S,
                            "weights_l2_persisting": True,
-                           "parallelism": f"dp{world} over clouds" + (", 1 NCCL all-gather of global descriptors per step (egn_allgather_global, "
-                                                                      "one communicator per stream)" if do_gather else
+                           "parallelism": f"dp{world} over clouds" + (", 1 NCCL all-gather of global descriptors per step (egn_allgather_global "
+                                                                      "on a communication stream per compute stream)" if do_gather else
                                                                       (", all-gather DISABLED (ablation)" if world > 1 else "")),
                            "clouds_total_per_step": clouds_total, "shard_imbalance_max_over_mean": imbalance},
                 "clocks": clocks,

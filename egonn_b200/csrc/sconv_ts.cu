@@ -7,15 +7,21 @@
 // shared-memory port and the instructions that feed it, not HBM and not the tensor pipe, bound the kernel
 // (profiles/r01_tc_kernel_stalls.md).  tcgen05.mma can take A from tensor memory ("TS" form), and tcgen05.st writes
 // registers straight into it, so here
-//   * producers : gather fp32 rows with 16-byte loads in the tcgen05.st.16x256b fragment layout (4 threads per row,
-//                 8 rows + 8 rows per warp instruction), split into bf16 hi/lo in registers, tcgen05.st both images
-//                 into a TMEM stage (64 columns: 32 hi + 32 lo).  No shared-memory traffic for A at all.
+//   * tiles     : 128 output rows taken from the level's TILE ROW ORDER (coords.cu: rows with similar offset sets are
+//                 adjacent, so whole (tile, chunk) pairs vanish); the prologue fetches slot -> row, then all table entries,
+//                 in two branch-free load batches, and compacts the list of non-empty chunks.
+//   * producers : gather rows with 256-bit loads in the tcgen05.st.16x256b fragment layout (4 threads per row,
+//                 8 rows + 8 rows per warp instruction), pre-split bf16 hi/lo maps move bits only (fp32 maps are split in
+//                 registers), tcgen05.st both images into a TMEM stage (64 columns: 32 hi + 32 lo).  No shared-memory
+//                 traffic for A at all.
 //                 A warp may only touch its own TMEM lane quarter, so a GROUP of 4 warps builds one chunk
 //                 (warp q -> rows 32q..32q+31); the 2 (or 4) groups of a CTA work on alternate chunks.
 //   * weights   : unchanged - pre-swizzled bf16 hi/lo images, one cp.async.bulk (TMA) pair per chunk into a ring.
 //   * MMA       : per chunk 4 K-steps x {hi*hi, lo*hi, hi*lo}, A = TMEM columns, B = shared-memory descriptor,
 //                 FP32 accumulators in TMEM columns [0, COUT); tcgen05.commit frees the stage.
-//   * epilogue  : tcgen05.ld -> folded BatchNorm scale/shift (+ReLU, +accumulate) -> the output row, written once.
+//   * epilogue  : tcgen05.ld -> the tile transposed through the idle weight ring in shared memory -> folded BatchNorm
+//                 scale/shift (+ReLU, +accumulate) -> whole output rows (512 contiguous bytes per warp instruction),
+//                 written once as fp32 or pre-split.
 // TMEM plan: COUT == 128: 1 CTA/SM, 512 columns = 128 accumulator + 6 stages x 64; otherwise 2 CTAs/SM, 256 columns
 // each = 64 accumulator + 3 stages x 64.  bf16x3 split (hi*hi + lo*hi + hi*lo), FP32 accumulation.
 // Gathers are 256-bit loads: lane j4 of a row reads channels 8*j4 .. 8*j4+7 of each 32-channel block, one L1 wavefront per
@@ -77,7 +83,13 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   const int row0 = blockIdx.x * kRows;
   const int col0 = blockIdx.y * COUT;     // N-split: this CTA computes output channels [col0, col0 + COUT)
   // debug timeline (EGN_TRACE=1, tools/trace_conv.py): clock64 stamps of one mid-grid CTA; a.trace is null in production
+  // The stamps cost ~12 instructions per chunk in the producers' loop, so they exist only in a -DEGN_TRACE_BUILD library
+  // (EGN_TRACE_BUILD=1 python -m egonn_b200.build --force).
+#ifdef EGN_TRACE_BUILD
   const bool trc = a.trace != nullptr && blockIdx.x == (gridDim.x >> 1) && blockIdx.y == 0 && blockIdx.z == 0;
+#else
+  constexpr bool trc = false;
+#endif
   if (trc && tid == 0) a.trace[60 * 8 + 0] = clock64();
 
   // neighbour rows of the tile: the global loads go out FIRST (their latency overlaps barrier setup and TMEM allocation),

@@ -120,9 +120,26 @@ class ShardedBatch:
         return max(self.loads) / (sum(self.loads) / len(self.loads)) if sum(self.loads) else 1.0
 
 
-def run_sharded(model, sb: ShardedBatch, group=None, comm: Optional[Communicator] = None) -> Tuple[torch.Tensor, Dict]:
+def on_side_stream(side: torch.cuda.Stream, fn, *tensors):
+    """Run ``fn()`` on ``side`` after everything enqueued so far on the current stream: the caller's stream goes on with
+    its next batch instead of waiting for the other ranks inside the collective.  ``tensors`` are inputs of ``fn`` that
+    the caching allocator must keep alive until ``side`` has used them."""
+    cur = torch.cuda.current_stream()
+    ev = torch.cuda.Event()
+    ev.record(cur)
+    side.wait_event(ev)
+    with torch.cuda.stream(side):
+        out = fn()
+    for t in tensors:
+        t.record_stream(side)
+    return out
+
+
+def run_sharded(model, sb: ShardedBatch, group=None, comm: Optional[Communicator] = None,
+                comm_stream: Optional[torch.cuda.Stream] = None) -> Tuple[torch.Tensor, Dict]:
     """Forward of this rank's share + the ONE all-gather of the path: (all global descriptors (B,256) in original cloud
-    order, this rank's packed local outputs with ``cloud_ids``)."""
+    order, this rank's packed local outputs with ``cloud_ids``).  With ``comm_stream`` the collective is issued there
+    (the result is then ready on THAT stream): a rank's compute stream never waits for the other ranks."""
     if sb.mine:
         local = model.forward_packed({"coords": sb.coords, "features": sb.features})
         g = local["global"]
@@ -130,6 +147,8 @@ def run_sharded(model, sb: ShardedBatch, group=None, comm: Optional[Communicator
         local, g = {}, torch.zeros((0, model.global_descriptor_size), device=sb.device)
     local["cloud_ids"] = sb.mine
     local["parts"] = sb.parts
+    if comm_stream is not None:
+        return on_side_stream(comm_stream, lambda: gather_global(g, sb.parts, group, comm), g), local
     return gather_global(g, sb.parts, group, comm), local
 
 

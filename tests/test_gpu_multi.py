@@ -68,6 +68,13 @@ def _worker(rank, world, port, out_path):
         ca = local["local_coords"][off_l[j]:off_l[j + 1], 1:]
         cb = full["local_coords"][off_f[i]:off_f[i + 1], 1:]
         assert torch.equal(ca, cb)
+    # the collective on a dedicated communication stream (what bench.py does: the compute stream never waits for other ranks)
+    side = torch.cuda.Stream(device=dev)
+    sb = parallel.ShardedBatch(coords, E.batched_coordinates, rank, world)
+    g_side, _ = parallel.run_sharded(model, sb, comm=comm, comm_stream=side)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    assert float((g_side - g_all).abs().max()) == 0.0
     # a second collective on the same communicator (steady-state use), padded shares
     g2 = parallel.gather_global(full["global"][torch.tensor(parts[rank], device=dev)], parts, comm=comm)
     assert float((g2 - full["global"]).abs().max()) == 0.0

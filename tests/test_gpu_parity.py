@@ -401,3 +401,42 @@ def test_batch_with_an_empty_cloud(cuda, weights):
     assert lp[2] == lp[1]                                             # no local rows for the empty cloud
     for b in (0, 2):
         assert_close_rel(part["descriptors"][lp[b]:lp[b + 1]], full["descriptors"][lo[b]:lo[b + 1]], 5e-5, f"descriptors of cloud {b}")
+
+
+def test_concurrent_host_threads_and_streams_match_serial(cuda, weights):
+    """One engine context per (device, CUDA stream): three host threads, each feeding its own stream (what bench.py does),
+    give bit-identical results to the same forwards issued serially."""
+    import threading
+    g = load_golden("mini3_cartesian")
+    quant = GOLDEN_CASES["mini3_cartesian"]
+    model, _ = _model(weights, quant, cuda)
+    base = torch.from_numpy(g["coords"]).to(cuda)
+    batches = []
+    for k in range(3):
+        c = base.clone()
+        c[:, 1] += 9 * k
+        batches.append({"coords": c, "features": torch.ones((c.shape[0], 1), device=cuda)})
+    serial = [model.forward_packed(b) for b in batches]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=cuda) for _ in range(3)]
+    out, errors = [None] * 3, []
+
+    def work(t):
+        try:
+            torch.cuda.set_device(cuda)
+            with torch.cuda.stream(streams[t]):
+                for _ in range(4):                                   # repeated: contexts are reused across steps
+                    out[t] = model.forward_packed(batches[t])
+        except BaseException as exc:
+            errors.append(exc)
+
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(3)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+    for t in range(3):
+        for k in ("global", "descriptors", "keypoints", "sigma", "local_coords"):
+            assert torch.equal(out[t][k], serial[t][k]), f"thread {t}: {k}"

@@ -1,6 +1,7 @@
 """Dump the clock64 timeline of one mid-grid CTA of a tensor-core convolution (EGN_TRACE=1; k_sconv_ts stamps).
 
-    python tools/trace_conv.py LEVEL CHANNELS             # one isolated 3x3x3 convolution at a cfg2 level, fp32 input map
+    EGN_TRACE_BUILD=1 python -m egonn_b200.build --force  # the stamps are compiled in only on request
+    python tools/trace_conv.py LEVEL CHANNELS [KSIZE]     # one isolated convolution at a cfg2 level, fp32 input map
 """
 import ctypes as C
 import os
