@@ -410,7 +410,7 @@ def main():
     eng = model._engine
 
     # ---- e2e arm ----
-    run_e2e(3)
+    run_e2e(max(3, 2 * S))                    # every host thread warms both of its staging slots
     barrier()
     t0 = time.perf_counter()
     run_e2e(K)
