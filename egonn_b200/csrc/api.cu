@@ -116,6 +116,7 @@ int egn_ctx_create(egn_ctx **out, int device) {
   if (const char *t = getenv("EGN_TRACE")) if (t[0] == '1') { cudaMalloc(&ctx->trace, 64 * 8 * 8); cudaMemset(ctx->trace, 0, 64 * 8 * 8); }
   if (const char *v = getenv("EGN_NSPLIT_MAX")) ctx->nsplit_max = atoi(v);
   if (const char *v = getenv("EGN_ORDER")) ctx->use_order = v[0] != '0';
+  if (const char *v = getenv("EGN_LIGHT")) ctx->light_ctas = v[0] != '0';
   if (const char *v = getenv("EGN_ORDER_WINDOW")) {
     const int w = atoi(v);
     if (w == 2048 || w == 4096 || w == 8192) ctx->order_window = w;

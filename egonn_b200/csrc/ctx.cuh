@@ -83,6 +83,7 @@ struct egn_ctx {
   egn::Taps taps;
   egn::Prof prof;
   bool use_tc = true;
+  bool light_ctas = true;           // short-tile convolutions as four light CTAs per SM (EGN_LIGHT=0 disables)
   bool use_order = true;            // mask-sorted tile row orders for the tensor-core convolutions (EGN_ORDER=0 disables)
   int order_window = 8192;          // rows are re-grouped inside windows of this many canonical rows (EGN_ORDER_WINDOW = 2048 | 4096 | 8192)
   // kernels already opted in to > 48 KB dynamic shared memory ON THIS CONTEXT'S DEVICE: the attribute is per device, a

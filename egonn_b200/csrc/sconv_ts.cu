@@ -35,19 +35,25 @@ namespace ts {
 
 using namespace tcx;
 
-template <int CIN, int COUT>
+// LIGHT: the row-wise layers (1x1x1: 1-2 chunks per tile, <= 64 output channels per CTA) spend most of a tile's life in the
+// prologue / first gather / epilogue chain, not in the chunk loop; they run FOUR small CTAs per SM (one producer group, one
+// TMEM stage, 128 TMEM columns, 192 threads) so that four of those chains overlap instead of two.
+template <int CIN, int COUT, int KOFF, bool LIGHT>
 struct Cfg {
   static constexpr bool kBig = COUT == 128;
   static constexpr bool kFold = COUT == 32;                // 2-instruction form: D[:, 0:64] += Ahi*[Bhi;Blo]^T, D[:, 0:32] += Alo*Bhi^T
-  static constexpr int kGroups = kBig ? 4 : 2;             // producer groups; one warp per TMEM lane quarter in each
+  static constexpr int kGroups = LIGHT ? 1 : (kBig ? 4 : 2);   // producer groups; one warp per TMEM lane quarter in each
   static constexpr int kProducerWarps = 4 * kGroups;
-  static constexpr int kStages = kBig ? 6 : 3;
-  static constexpr int kCtasPerSm = kBig ? 1 : 2;
-  static constexpr int kTmemCols = kBig ? 512 : 256;
+  static constexpr int kStages = LIGHT ? 1 : (kBig ? 6 : 3);
+  static constexpr int kCtasPerSm = LIGHT ? 4 : (kBig ? 1 : 2);
+  static constexpr int kTmemCols = LIGHT ? 128 : (kBig ? 512 : 256);
   static constexpr int kAccCols = kBig ? 128 : 64;         // A stages start here; accumulator = columns [0, COUT)
   static constexpr int kThreads = (kProducerWarps + 2) * 32;
   static constexpr int kBBytes = 2 * COUT * 128;           // hi + lo image of one weight chunk
-  static constexpr int kSmemBytes = kStages * kBBytes + kRows * 27 * 4 + 1536;
+  static constexpr int kTileBytes = kRows * COUT * 4;      // the fp32 output tile staged by the epilogue
+  static constexpr int kRingBytes = kStages * kBBytes > kTileBytes ? kStages * kBBytes : kTileBytes;
+  static constexpr int kSmemBytes = kRingBytes + kRows * KOFF * 4 + 1536;
+  static_assert(!LIGHT || COUT <= 64, "light CTAs: at most 64 output channels");
 };
 
 // SPLIT_IN: the input feature map is in the engine's pre-split format (common.cuh: every 4 channels = 16 bytes
@@ -57,20 +63,20 @@ struct Cfg {
 // MODE (compile time - a run-time switch in the prologue made the compiler emit a jump table per table entry and the
 // dependent loads of consecutive entries serialised: 5-10 k cycles per tile): 0 identity rows (1x1x1), 1 27-neighbour
 // table, 2 2x2x2 stride-2 children, 3 transposed 2x2x2 (parent row, kernel slice = the row's own child code).
-template <int CIN, int COUT, int KOFF, bool SPLIT_IN, int MODE>
-__global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCtasPerSm) k_sconv_ts(Args a) {
+template <int CIN, int COUT, int KOFF, bool SPLIT_IN, int MODE, bool LIGHT>
+__global__ void __launch_bounds__(Cfg<CIN, COUT, KOFF, LIGHT>::kThreads, Cfg<CIN, COUT, KOFF, LIGHT>::kCtasPerSm) k_sconv_ts(Args a) {
   // MODE 0 with KOFF == 2: a row-wise layer with 2 * CIN input channels - "offset" k reads channel block k of the same row
   // (the (n, 2 CIN) map viewed as (2 n, CIN): source row 2 r + k).
   static_assert((MODE == 0 && (KOFF == 1 || KOFF == 2)) || (MODE == 1 && KOFF == 27) || ((MODE == 2 || MODE == 3) && KOFF == 8), "mode / offsets");
-  using C = Cfg<CIN, COUT>;
+  using C = Cfg<CIN, COUT, KOFF, LIGHT>;
   constexpr int kStages = C::kStages, NG = C::kGroups;
   constexpr int NPW = C::kProducerWarps, NT = C::kThreads;
   constexpr int NCH = (KOFF * CIN + kChunk - 1) / kChunk;         // chunks if nothing is skipped
   constexpr int NBR_ITERS = (kRows * KOFF + NT - 1) / NT;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *btiles = smem;                                         // B ring: [kStages][hi | lo] (COUT*128 bytes each image)
-  int *s_nbr = (int *)(btiles + kStages * C::kBBytes);            // [kRows][KOFF]
-  uint64_t *full = (uint64_t *)(s_nbr + kRows * 27);              // [kStages]  A stage stored + weight chunk landed
+  int *s_nbr = (int *)(btiles + C::kRingBytes);                   // [kRows][KOFF]
+  uint64_t *full = (uint64_t *)(s_nbr + kRows * KOFF);            // [kStages]  A stage stored + weight chunk landed
   uint64_t *empty = full + kStages;                               // [kStages]  stage consumed by the tensor core
   uint64_t *accum = empty + kStages;                              // [1]
   uint32_t *s_tmem = (uint32_t *)(accum + 1);
@@ -321,7 +327,7 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
     // conflict-free both ways.
     constexpr int CPW = COUT / NG;                                           // accumulator columns per warp (>= 16)
     static_assert(CPW >= 16 && CPW % 16 == 0, "tcgen05.ld granularity: 16 columns");
-    static_assert(kStages * C::kBBytes >= kRows * COUT * 4, "the weight ring must hold one fp32 output tile");
+    static_assert(C::kRingBytes >= kRows * COUT * 4, "the weight ring region must hold one fp32 output tile");
     if (nlist > 0) {
       mbar_wait(accum, 0u, a.hint_producer);
       tc_fence_after();
@@ -449,14 +455,24 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::kThreads, Cfg<CIN, COUT>::kCta
   }
 }
 
-template <int CIN, int COUT, int KOFF, bool SPLIT_IN, int MODE>
-static int launch1(egn_ctx *ctx, const Args &a, const char *name, double bytes, double flops, cudaStream_t s) {
-  using C = Cfg<CIN, COUT>;
-  EGN_SMEM_OPTIN(ctx, (k_sconv_ts<CIN, COUT, KOFF, SPLIT_IN, MODE>), C::kSmemBytes);
+template <int CIN, int COUT, int KOFF, bool SPLIT_IN, int MODE, bool LIGHT>
+static int launch2(egn_ctx *ctx, const Args &a, const char *name, double bytes, double flops, cudaStream_t s) {
+  using C = Cfg<CIN, COUT, KOFF, LIGHT>;
+  EGN_SMEM_OPTIN(ctx, (k_sconv_ts<CIN, COUT, KOFF, SPLIT_IN, MODE, LIGHT>), C::kSmemBytes);
   const dim3 grid((unsigned)div_up(a.n_out, kRows), (unsigned)(a.cout_total / COUT), (unsigned)a.ksplit);
-  EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv_ts<CIN, COUT, KOFF, SPLIT_IN, MODE><<<grid, C::kThreads, C::kSmemBytes, s>>>(a));
+  EGN_LAUNCH(ctx, name, bytes, flops, s, k_sconv_ts<CIN, COUT, KOFF, SPLIT_IN, MODE, LIGHT><<<grid, C::kThreads, C::kSmemBytes, s>>>(a));
   EGN_CUDA(cudaGetLastError());
   return EGN_OK;
+}
+
+template <int CIN, int COUT, int KOFF, bool SPLIT_IN, int MODE>
+static int launch1(egn_ctx *ctx, const Args &a, const char *name, double bytes, double flops, cudaStream_t s) {
+  // row-wise layers (1-2 chunks per tile): four light CTAs per SM, measured -5 % on the class (EGN_LIGHT=0: the standard shape);
+  // the stride-2 / transposed convolutions (2-4 chunks) lose 6-8 % with a single producer group and stay standard
+  if constexpr (MODE == 0 && COUT <= 64) {
+    if (ctx->light_ctas) return launch2<CIN, COUT, KOFF, SPLIT_IN, MODE, true>(ctx, a, name, bytes, flops, s);
+  }
+  return launch2<CIN, COUT, KOFF, SPLIT_IN, MODE, false>(ctx, a, name, bytes, flops, s);
 }
 
 template <int CIN, int COUT, int KOFF, int MODE>
