@@ -13,10 +13,10 @@ KITTI-64-beam-shaped clouds, 0.10 m voxels, per GPU: weak scaling).
           in rotation exceed the L2 (config.input_rotation); every step also writes ~1 GB of fresh activations.
           value_l2_flush is the round-1 protocol for continuity: same loop with a 256 MiB memset before every step
           INSIDE the timed region.
-  e2e   : same metric through the public API (model.forward_points) from pinned HOST point clouds: H2D of the raw
-          points, fused GPU quantisation + pyramid, forward, keypoint selection, D2H of global descriptors + top-256
-          keypoints and their descriptors - all inside the timed region (wall clock, sync on both sides; the H2D
-          of step i+1 runs on a copy stream while step i computes).
+  e2e   : same metric through the public pipeline API (egonn_b200.Extractor.extract) from pinned HOST point clouds:
+          H2D of the raw points, fused GPU quantisation + pyramid, forward, keypoint selection, D2H of global
+          descriptors + top-256 keypoints and their descriptors - all inside the timed region (wall clock, sync on
+          both sides; one host thread per stream, two batches in flight per thread).
   roofline     : dominant kernel class by device time (live CUDA-event brackets inside the engine).
   cpu_baseline : the ME-semantics CPU oracle (oracle/, torch CPU, all host threads) on a bounded sample.
 --impl reference times that CPU oracle as the reference arm (MinkowskiEngine itself cannot be installed).
@@ -322,66 +322,24 @@ def main():
         torch.cuda.synchronize()
         return start.elapsed_time(end)
 
-    # ---- host-resident raw clouds (the `e2e` arm): pinned host points -> H2D -> fused quantise+pyramid -> forward ->
-    #      top-k -> D2H of global descriptors, top-256 keypoints and their descriptors.  Two device slots: the H2D of step
-    #      i+1 (copy stream) overlaps the compute of step i; every byte of every step moves inside the timed region. ----
-    #      ONE pinned staging buffer per direction: [points of all clouds | first-point offsets] goes up in one copy, the
-    #      packed [global | keypoints | descriptors] rows of all clouds (egn_pack_topk) come down in one copy.
-    n_pts = int(sum(pc.shape[0] for pc in clouds))
-    starts = np.cumsum([0] + [pc.shape[0] for pc in clouds]).astype(np.int32)
-    stage_words = n_pts * 3 + batch + 1
-    host_in = torch.empty((stage_words,), dtype=torch.float32).pin_memory()
-    host_in[: n_pts * 3] = torch.from_numpy(np.concatenate(clouds, axis=0).reshape(-1))
-    host_in[n_pts * 3:] = torch.from_numpy(starts).view(torch.float32)
-    h2d_bytes = stage_words * 4
-    NS = 2 * S                                            # two device / host slots per compute stream (= host thread)
-    dev_in = [torch.empty((stage_words,), dtype=torch.float32, device=dev) for _ in range(NS)]
-    dev_pts = [t[: n_pts * 3].view(n_pts, 3) for t in dev_in]
-    dev_off = [t[n_pts * 3:].view(torch.int32) for t in dev_in]
+    # ---- host-resident raw clouds (the `e2e` arm), through the public pipeline API (egonn_b200.Extractor): pinned host
+    #      points -> ONE H2D copy ([points | first-point offsets], staged once by stage_batch) -> fused quantise + pyramid ->
+    #      forward -> top-k -> egn_pack_topk -> ONE D2H copy of the packed [global | keypoints | descriptors] rows; one host
+    #      thread, copy stream and two staging slots per compute stream; every byte of every step moves inside the timed
+    #      region; results are delivered (and dropped) in order.  Weak multi-GPU runs all-gather every batch's global
+    #      descriptors through the extractor's communicators; the strong-scaling e2e arm has no collective (uneven shares).
+    staged = E.stage_batch(clouds)
+    h2d_bytes = staged.words * 4
     per_cloud = 256 + TOPK * 3 + TOPK * 128
-    dev_out = [torch.empty((batch, per_cloud), dtype=torch.float32, device=dev) for _ in range(NS)]
-    host_out = [torch.empty((batch, per_cloud), dtype=torch.float32).pin_memory() for _ in range(NS)]
-    d2h_bytes = batch * per_cloud * 4
-    copy_streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
-    ev_h2d = [torch.cuda.Event() for _ in range(NS)]
-    ev_done = [torch.cuda.Event() for _ in range(NS)]
-    for e in ev_done:
-        e.record()
-    torch.cuda.synchronize()
-
-    def enqueue_h2d(slot, t):
-        with torch.cuda.stream(copy_streams[t]):
-            copy_streams[t].wait_event(ev_done[slot])          # the previous user of this slot has finished
-            dev_in[slot].copy_(host_in, non_blocking=True)     # ONE host-to-device copy per step
-            ev_h2d[slot].record(copy_streams[t])
-
-    def step_e2e(i, t, n_steps):
-        """One end-to-end step of host thread t: ONE host-to-device copy of the raw points (on the thread's copy stream,
-        issued one step ahead into its other slot), fused quantise + pyramid, forward, top-k, pack, ONE device-to-host copy."""
-        j = i // S                                             # the thread's own step counter
-        slot = 2 * t + (j & 1)
-        if j == 0:
-            enqueue_h2d(slot, t)
-        if i + S < n_steps:
-            enqueue_h2d(2 * t + ((j + 1) & 1), t)              # next step's points travel while this step computes
-        cur = torch.cuda.current_stream()
-        cur.wait_event(ev_h2d[slot])
-        p = model.forward_points(dev_pts[slot], dev_off[slot])
-        idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK)
-        E.pack_topk(idx, p["local_offsets"], p["keypoints"], p["descriptors"], p["global"], out=dev_out[slot])
-        host_out[slot].copy_(dev_out[slot], non_blocking=True)   # ONE device-to-host copy per step
-        if do_gather:
-            g = p["global"]
-            if args.strong:
-                parallel.on_side_stream(comm_streams[t], lambda: parallel.gather_global(g, sb.parts, comm=comms[t]), g)
-            else:
-                buf = gathered[t]
-                parallel.on_side_stream(comm_streams[t], lambda: comms[t].all_gather(g, buf), g)
-        ev_done[slot].record(cur)
+    d2h_bytes = batch * per_cloud * 4 + (batch + 1) * 4
+    extractor = E.Extractor(model, streams=S, topk=TOPK, device=dev, comms=comms if (do_gather and not args.strong) else None)
 
     def run_e2e(n_steps):
-        run_workers(lambda i, t: step_e2e(i, t, n_steps), n_steps)
+        n_out = 0
+        for res in extractor.extract(staged for _ in range(n_steps)):
+            n_out += res["global"].shape[0]
         torch.cuda.synchronize()
+        assert n_out == n_steps * batch
 
     def barrier():
         if world > 1:

@@ -16,3 +16,4 @@ from .quantization import CartesianQuantizer, PolarQuantizer, batched_coordinate
 from .engine import Engine, topk_smallest, pack_topk, knn_global, match_descriptors, filter_points  # noqa: F401
 
 __version__ = "0.1.0"
+from .pipeline import Extractor, StagedBatch, stage_batch  # noqa: F401,E402
