@@ -33,6 +33,7 @@ from __future__ import annotations
 import argparse
 import json
 import os
+import queue
 import subprocess
 import sys
 import threading
@@ -274,28 +275,49 @@ def main():
         idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK)
         return p, idx
 
-    def run_workers(fn, n_steps):
-        """S host threads, one per compute stream: thread t issues steps t, t+S, ...  A step blocks its host thread once
-        (the row counts of egn_coords_build must reach the host); with one thread per stream the other streams keep being
-        fed meanwhile (ctypes releases the GIL inside the C ABI)."""
-        errors = []
+    class Workers:
+        """S persistent host threads, one per compute stream: thread t issues steps t, t+S, ...  A step blocks its host thread
+        once (the row counts of egn_coords_build must reach the host); with one thread per stream the other streams keep
+        being fed meanwhile (ctypes releases the GIL inside the C ABI)."""
 
-        def work(t):
-            try:
-                torch.cuda.set_device(dev)
-                with torch.cuda.stream(streams[t]):
-                    for i in range(t, n_steps, S):
-                        fn(i, t)
-            except BaseException as exc:                                          # surfaced by the main thread
-                errors.append(exc)
+        def __init__(self):
+            self.jobs = [queue.Queue() for _ in range(S)]
+            self.results = queue.Queue()
+            self.threads = [threading.Thread(target=self._work, args=(t,), daemon=True) for t in range(S)]
+            for th in self.threads:
+                th.start()
 
-        threads = [threading.Thread(target=work, args=(t,)) for t in range(S)]
-        for th in threads:
-            th.start()
-        for th in threads:
-            th.join()
-        if errors:
-            raise errors[0]
+        def _work(self, t):
+            torch.cuda.set_device(dev)
+            with torch.cuda.stream(streams[t]):
+                while True:
+                    job = self.jobs[t].get()
+                    if job is None:
+                        return
+                    fn, n_steps = job
+                    try:
+                        for i in range(t, n_steps, S):
+                            fn(i, t)
+                        self.results.put(None)
+                    except BaseException as exc:                                  # surfaced by the main thread
+                        self.results.put(exc)
+
+        def run(self, fn, n_steps):
+            for q in self.jobs:
+                q.put((fn, n_steps))
+            errs = [self.results.get() for _ in range(S)]
+            for e in errs:
+                if e is not None:
+                    raise e
+
+        def close(self):
+            for q in self.jobs:
+                q.put(None)
+            for th in self.threads:
+                th.join()
+
+    workers = Workers()
+    run_workers = workers.run
 
     def run_device(n_steps, do_flush=False):
         """n_steps steps over S streams (one engine context and one host thread each): a batch's small upper pyramid
@@ -454,6 +476,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, sd)
         print(json.dumps(line))
+    workers.close()
+    extractor.close()
     if world > 1:
         dist.barrier()
         for c in comms:

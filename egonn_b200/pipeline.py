@@ -162,22 +162,24 @@ class Extractor:
                 "descriptors": out[:, g + 3 * k:].reshape(b, k, d).clone(), "n_keypoints": (off[1:] - off[:-1]).clamp(max=k).clone()}
 
     # -- the pipeline ---------------------------------------------------------------------------------------
-    def extract(self, batches: Iterable[Batch]) -> Iterator[Dict[str, torch.Tensor]]:
-        """Yields results in submission order; at most 2 * streams batches are in flight."""
-        works = [queue.Queue() for _ in range(self.S)]    # batch i goes to stream i % S (deterministic: collectives pair up)
-        done: Dict[int, object] = {}
-        cond = threading.Condition()
+    def _ensure_workers(self):
+        """Worker threads live as long as the extractor (started at the first extract(), stopped by close())."""
+        if getattr(self, "_threads", None):
+            return
+        self._works = [queue.Queue() for _ in range(self.S)]   # batch i goes to stream i % S (deterministic: collectives pair up)
+        self._done: Dict[int, object] = {}
+        self._cond = threading.Condition()
 
         def deliver(seq, res):
-            with cond:
-                done[seq] = res
-                cond.notify_all()
+            with self._cond:
+                self._done[seq] = res
+                self._cond.notify_all()
 
         def worker(t: int):
             """Two batches in flight per thread: batch j+1 is enqueued (its points travel, its kernels queue) before the
             thread waits for batch j's results."""
             torch.cuda.set_device(self.device)
-            work = works[t]
+            work = self._works[t]
             j, pending = 0, None                           # pending = (seq, handle) enqueued but not yet delivered
             with torch.cuda.stream(self.streams[t]):
                 while True:
@@ -194,13 +196,13 @@ class Extractor:
                             except BaseException as exc:
                                 deliver(seq, exc)
                             continue
+                    new = None
                     if item is not None:
                         seq, clouds = item
                         try:
                             new = (seq, self._launch(t, self.slots[t][j & 1], clouds))
                         except BaseException as exc:       # delivered to the consumer in order
                             deliver(seq, exc)
-                            new = None
                         j += 1
                     if pending is not None:
                         pseq, h = pending
@@ -212,10 +214,31 @@ class Extractor:
                         return
                     pending = new
 
-        threads = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(self.S)]
-        for th in threads:
+        self._threads = [threading.Thread(target=worker, args=(t,), daemon=True) for t in range(self.S)]
+        for th in self._threads:
             th.start()
-        submitted = delivered = 0
+
+    def close(self):
+        if getattr(self, "_threads", None):
+            for w in self._works:
+                w.put(None)
+            for th in self._threads:
+                th.join()
+            self._threads = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def extract(self, batches: Iterable[Batch]) -> Iterator[Dict[str, torch.Tensor]]:
+        """Yields results in submission order; at most 2 * streams batches are in flight.  One extract() at a time."""
+        self._ensure_workers()
+        with self._cond:
+            self._done.clear()
+        base = getattr(self, "_seq_base", 0)               # sequence numbers keep growing: batch i -> stream i % S across calls
+        submitted = delivered = base
         try:
             it = iter(batches)
             exhausted = False
@@ -226,19 +249,23 @@ class Extractor:
                     except StopIteration:
                         exhausted = True
                         break
-                    works[submitted % self.S].put((submitted, clouds))
+                    self._works[submitted % self.S].put((submitted, clouds))
                     submitted += 1
                 if delivered < submitted:
-                    with cond:
-                        while delivered not in done:
-                            cond.wait()
-                        res = done.pop(delivered)
+                    with self._cond:
+                        while delivered not in self._done:
+                            self._cond.wait()
+                        res = self._done.pop(delivered)
                     delivered += 1
                     if isinstance(res, BaseException):
                         raise res
                     yield res
         finally:
-            for w in works:
-                w.put(None)
-            for th in threads:
-                th.join()
+            # batches still in flight (the consumer stopped early, or an error was raised) are drained and dropped
+            while delivered < submitted:
+                with self._cond:
+                    while delivered not in self._done:
+                        self._cond.wait()
+                    self._done.pop(delivered)
+                delivered += 1
+            self._seq_base = submitted
