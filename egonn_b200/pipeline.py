@@ -91,7 +91,8 @@ class Extractor:
 
     # -- staging ------------------------------------------------------------------------------------------
     def _stage(self, slot: _Slot, clouds: Batch):
-        """Returns (host staging buffer, points, clouds, words); a StagedBatch is used as it is (no host copy)."""
+        """Returns (host staging buffer, points, clouds, words, device buffer freshly allocated); a StagedBatch is used as it
+        is (no host copy)."""
         if isinstance(clouds, StagedBatch):
             sb = clouds
         else:
@@ -100,13 +101,14 @@ class Extractor:
                 slot.host_in = torch.empty((int(sb.words * 1.25) + 64,), dtype=torch.float32).pin_memory()
             slot.host_in[: sb.words].copy_(sb.buf)                    # ... and moved into the slot's pinned buffer
             sb = StagedBatch(slot.host_in, sb.n_points, sb.n_clouds)
-        if slot.dev_in is None or slot.dev_in.numel() < sb.words:
+        fresh = slot.dev_in is None or slot.dev_in.numel() < sb.words
+        if fresh:
             slot.dev_in = torch.empty((int(sb.words * 1.25) + 64,), dtype=torch.float32, device=self.device)
         per = self.gdim + self.topk * (3 + self.ddim)
         if slot.host_out is None or slot.host_out.shape[0] < sb.n_clouds:
             slot.host_out = torch.empty((sb.n_clouds, per), dtype=torch.float32).pin_memory()
             slot.dev_out = torch.empty((sb.n_clouds, per), dtype=torch.float32, device=self.device)
-        return sb.buf, sb.n_points, sb.n_clouds, sb.words
+        return sb.buf, sb.n_points, sb.n_clouds, sb.words, fresh
 
     def _launch(self, t: int, slot: _Slot, clouds: Batch):
         """Enqueue one batch on stream t (no host wait): H2D on the thread's copy stream, ingest + forward + top-k + pack on
@@ -114,7 +116,11 @@ class Extractor:
         cur, cs = self.streams[t], self.copy_streams[t]
         if slot.done is not None:
             slot.done.synchronize()                        # the slot's previous batch has left the device
-        host_in, total, b, words = self._stage(slot, clouds)
+        host_in, total, b, words, fresh = self._stage(slot, clouds)
+        if fresh:
+            # the caching allocator may have recycled a block that kernels still queued on the COMPUTE stream write (outputs of
+            # the previous batch, freed on the host already): the copy stream must not write it before they have run
+            cs.wait_stream(cur)
         with torch.cuda.stream(cs):
             slot.dev_in[:words].copy_(host_in[:words], non_blocking=True)          # ONE host-to-device copy
             up = torch.cuda.Event()
