@@ -23,8 +23,9 @@ KITTI-64-beam-shaped clouds, 0.10 m voxels, per GPU: weak scaling).
 
 Multi-GPU (torchrun, one process per GPU): weak scaling by default (every rank extracts its own --batch clouds); the ONE
 collective of the path - the all-gather of the (clouds, 256) global descriptors - is issued through the engine's own
-NCCL communicator (egn_allgather_global) on a dedicated communication stream behind an event of the step: a rank's
-compute streams never wait for the other ranks; the timed region ends after the last gather.  --strong runs the
+NCCL communicator (egn_allgather_global) by ONE host thread on ONE communication stream in step order
+(parallel.OrderedGatherer), behind an event of the step: a rank's compute streams never wait for the other ranks; the
+timed region ends after the last gather.  --strong runs the
 config's TOTAL batch (cfg4: 256 clouds) sharded over the ranks by egonn_b200.parallel (greedy balance by voxel count,
 original order restored after the gather); --no-gather is the ablation that drops the collective.
 """
@@ -195,9 +196,20 @@ def main():
         run_reference(args, rank, world)
         return
 
+    import faulthandler
     import torch.distributed as dist
     import egonn_b200 as E
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path)"
+
+    def watchdog(phase):
+        """A phase that makes no progress for minutes (a collective whose peers never arrive) ends the process with every
+        thread's traceback on stderr instead of hanging the box until the caller's limit."""
+        faulthandler.cancel_dump_traceback_later()
+        if phase is not None:
+            print(f"[bench rank {rank}] {phase}", file=sys.stderr, flush=True)
+            faulthandler.dump_traceback_later(300 + 0.05 * args.steps, exit=True)
+
+    watchdog("setup")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -216,13 +228,14 @@ def main():
     S = max(1, args.streams)
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)]
     do_gather = world > 1 and not args.no_gather
-    # the engine's own NCCL communicator on a dedicated communication stream: a step hands its global descriptors over with
-    # an event and its compute stream goes on with the next batch - it never waits for the other ranks inside the
-    # collective (every rank issues the gathers in step order, so one communicator serves all compute streams)
-    # (one communicator + side stream per compute stream / host thread: thread t runs steps t, t+S, ... on every rank, so
-    # the gathers of a communicator pair up step for step)
-    comms = [parallel.Communicator(dev) for _ in range(S)] if do_gather else []
-    comm_streams = [torch.cuda.Stream(device=dev) for _ in range(S)] if do_gather else []
+    # the ONE collective of the path through the engine's own NCCL communicator.  One communicator, one communication
+    # stream, one issuing host thread, the same (step) order on every rank: parallel.OrderedGatherer.  The worker threads
+    # hand their global descriptors over with an event and go on; they never wait for the other ranks.  (One communicator
+    # per compute stream deadlocked at N = 8: NCCL kernels of different communicators waiting for each other across GPUs.)
+    comm = parallel.Communicator(dev) if do_gather else None
+    comms = [comm] if comm is not None else []
+    gatherer = parallel.OrderedGatherer(dev) if do_gather else None
+    ticket_base = [0]
 
     # ---- device-resident voxelised batch (the `value` arm) ----
     imbalance = None
@@ -259,19 +272,14 @@ def main():
     def step_device(i, t):
         """Step i on compute stream t (the current stream of the calling thread)."""
         bc = rot_coords[i % NB]
-        if args.strong:
-            if do_gather:
-                share = parallel.ShardedBatch.__new__(parallel.ShardedBatch)      # this step's view of the share: rotated coordinates
-                share.__dict__.update(sb.__dict__)
-                share.coords = bc
-                g_all, p = parallel.run_sharded(model, share, comm=comms[t], comm_stream=comm_streams[t])
+        p = model.forward_packed({"coords": bc, "features": feats})
+        if do_gather:
+            g = p["global"]
+            if args.strong:                                   # uneven shares: padded gather + original cloud order (parallel.gather_global)
+                gatherer.submit(ticket_base[0] + i, lambda: parallel.gather_global(g, sb.parts, comm=comm), g)
             else:
-                p = model.forward_packed({"coords": bc, "features": feats})
-        else:
-            p = model.forward_packed({"coords": bc, "features": feats})
-            if do_gather:
-                g, buf = p["global"], gathered[t]
-                parallel.on_side_stream(comm_streams[t], lambda: comms[t].all_gather(g, buf), g)
+                buf = gathered[t]
+                gatherer.submit(ticket_base[0] + i, lambda: comm.all_gather(g, buf), g)
         idx = E.topk_smallest(p["sigma"], p["local_offsets"], TOPK)
         return p, idx
 
@@ -336,7 +344,13 @@ def main():
             step_device(i, t)
 
         run_workers(one, n_steps)
-        for st in streams + comm_streams:
+        comm_side = []
+        if gatherer is not None:                              # every gather of the region has been enqueued, then waited for
+            gatherer.drain(ticket_base[0] + n_steps)
+            ticket_base[0] += n_steps
+            gatherer.forget_results()
+            comm_side = [gatherer.stream]
+        for st in streams + comm_side:
             e = torch.cuda.Event()
             e.record(st)
             cur.wait_event(e)
@@ -354,7 +368,7 @@ def main():
     h2d_bytes = staged.words * 4
     per_cloud = 256 + TOPK * 3 + TOPK * 128
     d2h_bytes = batch * per_cloud * 4 + (batch + 1) * 4
-    extractor = E.Extractor(model, streams=S, topk=TOPK, device=dev, comms=comms if (do_gather and not args.strong) else None)
+    extractor = E.Extractor(model, streams=S, topk=TOPK, device=dev, comm=comm if (do_gather and not args.strong) else None)
 
     def run_e2e(n_steps):
         n_out = 0
@@ -368,6 +382,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    watchdog("warm-up")
     run_device(max(W, S))
     barrier()
 
@@ -377,6 +392,7 @@ def main():
     engines = list(model._engines.values())
     launches0 = sum(e.launch_count() for e in engines)
     barrier()
+    watchdog("timed region (value)")
     t_wall0 = time.perf_counter()
     total_ms = run_device(K)
     barrier()
@@ -384,12 +400,14 @@ def main():
 
     engines = list(model._engines.values())
     launches = (sum(e.launch_count() for e in engines) - launches0) / K + 1        # + the top-k kernel of every step (NCCL's kernel not counted)
+    watchdog("value_l2_flush")
     flush_ms = run_device(K, do_flush=True) / K         # round-1 protocol, for continuity
     barrier()
     ms_step = float(total_ms / K)
     eng = model._engine
 
     # ---- e2e arm ----
+    watchdog("e2e")
     run_e2e(max(3, 2 * S))                    # every host thread warms both of its staging slots
     barrier()
     t0 = time.perf_counter()
@@ -399,6 +417,7 @@ def main():
     clocks = sampler.stop()
 
     # ---- per-kernel-class profile (separate pass so the event brackets do not perturb the timed region) ----
+    watchdog("per-kernel profile pass")
     with torch.cuda.stream(streams[0]):             # every rank: same stream, same number of steps (the collective stays in order)
         step_device(0, 0)
         eng = model._engine
@@ -406,6 +425,10 @@ def main():
         for j in range(min(K, 10)):
             flush.zero_()
             step_device(j + 1, 0)
+        if gatherer is not None:
+            gatherer.drain(ticket_base[0] + min(K, 10) + 1)
+            ticket_base[0] += min(K, 10) + 1
+            gatherer.forget_results()
         torch.cuda.synchronize()
         prof = eng.profile_read()
         eng.profile(False)
@@ -460,8 +483,8 @@ def main():
                                                       "value_l2_flush repeats the round-1 protocol (256 MiB memset per step inside the timed region)"},
                            "streams_per_gpu": S, "host_threads_per_gpu": S,
                            "weights_l2_persisting": True,
-                           "parallelism": f"dp{world} over clouds" + (", 1 NCCL all-gather of global descriptors per step (egn_allgather_global "
-                                                                      "on a communication stream per compute stream)" if do_gather else
+                           "parallelism": f"dp{world} over clouds" + (", 1 NCCL all-gather of global descriptors per step (egn_allgather_global: one "
+                                                                      "communicator, one communication stream, step order)" if do_gather else
                                                                       (", all-gather DISABLED (ablation)" if world > 1 else "")),
                            "clouds_total_per_step": clouds_total, "shard_imbalance_max_over_mean": imbalance},
                 "clocks": clocks,
@@ -474,15 +497,25 @@ def main():
             with open(args.profile_out, "w") as f:
                 json.dump({"kernels": table, "ms_per_step_profiled": total_ms / n_prof}, f, indent=1)
         if world == 1 and not args.no_cpu_baseline:
+            watchdog("cpu_baseline")
             line["cpu_baseline"] = cpu_baseline(args, sd)
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    # the measurement is complete and printed: a teardown that does not return (a peer that already left its communicator)
+    # must not turn into a hang or a failure
+    watchdog(None)
+    guard = threading.Timer(60.0, lambda: os._exit(0))
+    guard.daemon = True
+    guard.start()
     workers.close()
     extractor.close()
+    if gatherer is not None:
+        gatherer.close()
     if world > 1:
         dist.barrier()
         for c in comms:
             c.close()
         dist.destroy_process_group()
+    guard.cancel()
 
 
 def cpu_baseline(args, sd):

@@ -35,6 +35,13 @@ class Communicator:
         ident = (C.c_ubyte * 128).from_buffer_copy(box[0])
         self._comm = C.c_void_p()
         L.check(self.lib.egn_comm_create(C.byref(self._comm), self.device.index or 0, self.rank, self.world, ident))
+        # NCCL connects its peers lazily, inside the first collective of a communicator (host-side rendezvous of all ranks
+        # plus device allocations).  Do that here, where every rank is at the same program point and nothing else runs,
+        # not inside a pipeline of worker threads.
+        with torch.cuda.device(self.device):
+            warm = torch.zeros((1, 32), dtype=torch.float32, device=self.device)
+            self.all_gather(warm)
+            torch.cuda.current_stream(self.device).synchronize()
 
     def all_gather(self, send: torch.Tensor, recv: Optional[torch.Tensor] = None) -> torch.Tensor:
         """recv (world * n, D) <- send (n, D) of every rank, rank order, on the current CUDA stream."""
@@ -95,6 +102,108 @@ def gather_global(local: torch.Tensor, parts: List[List[int]], group=None, comm:
         if p:
             out[torch.tensor(p, device=local.device, dtype=torch.long)] = buf[r * bmax: r * bmax + len(p)]
     return out
+
+
+class OrderedGatherer:
+    """The collectives of one process, issued by ONE host thread on ONE CUDA stream through ONE communicator, in ticket
+    order - whatever the order in which the worker threads finish their steps.
+
+    NCCL kernels wait for their peers on the device, so collectives of different communicators (or of one communicator in
+    different orders on different ranks) that run concurrently on a GPU can wait for each other across GPUs for ever; an
+    8-GPU run with one communicator per compute stream did exactly that.  The safe shape is the classic one: a single
+    communicator, a single stream, the same order on every rank.  Worker threads ``submit(ticket, fn, *tensors)`` after
+    enqueueing the producer of ``tensors`` on their own stream; the gather thread runs ``fn()`` (which calls
+    ``comm.all_gather`` / ``gather_global``) on the communication stream behind an event, strictly by ascending ticket.
+    Every rank must use the same tickets (consecutive integers) - e.g. the global step number."""
+
+    def __init__(self, device: torch.device, first_ticket: int = 0):
+        import threading
+        self.device = torch.device(device)
+        self.stream = self._make_stream()
+        self._cv = threading.Condition()
+        self._pending: Dict[int, tuple] = {}
+        self._results: Dict[int, object] = {}
+        self._next = first_ticket
+        self._closed = False
+        self._error: Optional[BaseException] = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    # CUDA plumbing, overridable (the CPU unit test replaces these three)
+    def _make_stream(self):
+        return torch.cuda.Stream(device=self.device)
+
+    def _record_event(self):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        return ev
+
+    def _run_on_stream(self, ev, fn, tensors):
+        torch.cuda.set_device(self.device)
+        self.stream.wait_event(ev)
+        with torch.cuda.stream(self.stream):
+            out = fn()
+        for t in tensors:
+            t.record_stream(self.stream)
+        return out
+
+    def submit(self, ticket: int, fn, *tensors):
+        """Called by a worker thread right after it has enqueued the producer of ``tensors`` on its current stream.
+        ``fn is None`` consumes the ticket without a collective (a step that failed must still release its successors)."""
+        ev = self._record_event() if fn is not None else None
+        with self._cv:
+            assert ticket >= self._next and ticket not in self._pending, f"ticket {ticket} submitted twice or too late"
+            self._pending[ticket] = (ev, fn, tensors)
+            self._cv.notify_all()
+
+    def result(self, ticket: int):
+        """Blocks until the collective of ``ticket`` has been ENQUEUED on the communication stream; returns what ``fn``
+        returned (tensors that are ready on ``self.stream``)."""
+        with self._cv:
+            while ticket not in self._results and self._error is None:
+                self._cv.wait()
+            if self._error is not None:
+                raise self._error
+            return self._results.pop(ticket)
+
+    def drain(self, up_to: int):
+        """Blocks until every ticket below ``up_to`` has been enqueued (host side; synchronise ``self.stream`` for the device)."""
+        with self._cv:
+            while self._next < up_to and self._error is None:
+                self._cv.wait()
+            if self._error is not None:
+                raise self._error
+
+    def _run(self):
+        while True:
+            with self._cv:
+                while self._next not in self._pending and not self._closed:
+                    self._cv.wait()
+                if self._closed and self._next not in self._pending:
+                    return
+                ticket = self._next
+                ev, fn, tensors = self._pending.pop(ticket)
+            try:
+                out = self._run_on_stream(ev, fn, tensors) if fn is not None else None
+            except BaseException as exc:                      # surfaced to whoever waits
+                with self._cv:
+                    self._error = exc
+                    self._cv.notify_all()
+                return
+            with self._cv:
+                self._results[ticket] = out
+                self._next = ticket + 1
+                self._cv.notify_all()
+
+    def forget_results(self):
+        with self._cv:
+            self._results.clear()
+
+    def close(self):
+        with self._cv:
+            self._closed = True
+            self._cv.notify_all()
+        self._thread.join()
 
 
 class ShardedBatch:

@@ -57,7 +57,7 @@ class _Slot:
         self.host_out: Optional[torch.Tensor] = None     # pinned packed result
         self.host_off: Optional[torch.Tensor] = None     # pinned per-cloud row offsets of the local level
         self.host_all: Optional[torch.Tensor] = None     # pinned all-gathered global descriptors (multi-GPU)
-        self.gather_done = None
+        self.gather_ticket = None
         self.done = None                                 # event: the slot's last device work has finished
 
 
@@ -68,12 +68,11 @@ class Extractor:
     or of ``StagedBatch`` objects (``stage_batch(clouds)``: already pinned and laid out, no host copy in the pipeline).
     The model must live on a CUDA device (there is no CPU path)."""
 
-    def __init__(self, model, streams: int = 4, topk: int = 256, device: Optional[torch.device] = None,
-                 comms: Optional[Sequence] = None):
-        """``comms``: one ``egonn_b200.parallel.Communicator`` per stream (multi-GPU, one process per GPU): every batch's
-        global descriptors are all-gathered over the ranks (``egn_allgather_global`` on a side stream) and returned as
-        ``global_all (world * B, G)``; every rank must then submit batches of the same cloud count in the same order
-        (batch i is handled by stream i % streams on every rank, so the collectives pair up)."""
+    def __init__(self, model, streams: int = 4, topk: int = 256, device: Optional[torch.device] = None, comm=None):
+        """``comm``: an ``egonn_b200.parallel.Communicator`` (multi-GPU, one process per GPU): every batch's global
+        descriptors are all-gathered over the ranks (``egn_allgather_global``) and returned as ``global_all (world * B, G)``.
+        The collectives are issued by one thread on one stream in batch order (``parallel.OrderedGatherer``); every rank
+        must submit batches of the same cloud count in the same order, and nothing else may use ``comm`` meanwhile."""
         p = next(model.parameters())
         if not p.is_cuda:
             raise RuntimeError("egonn_b200 has no CPU path: move the model to a CUDA device first")
@@ -84,9 +83,8 @@ class Extractor:
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(self.S)]
         self.copy_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.S)]
         self.slots = [[_Slot(), _Slot()] for _ in range(self.S)]
-        self.comms = list(comms) if comms else None
-        assert self.comms is None or len(self.comms) == self.S, "one communicator per stream"
-        self.comm_streams = [torch.cuda.Stream(device=self.device) for _ in range(self.S)] if self.comms else []
+        self.comm = comm
+        self.gatherer = None                               # parallel.OrderedGatherer, created with the worker threads
         model._pack(self.device)                           # weights packed before the worker threads start
 
     # -- staging ------------------------------------------------------------------------------------------
@@ -110,7 +108,7 @@ class Extractor:
             slot.dev_out = torch.empty((sb.n_clouds, per), dtype=torch.float32, device=self.device)
         return sb.buf, sb.n_points, sb.n_clouds, sb.words, fresh
 
-    def _launch(self, t: int, slot: _Slot, clouds: Batch):
+    def _launch(self, t: int, slot: _Slot, clouds: Batch, seq: int = 0):
         """Enqueue one batch on stream t (no host wait): H2D on the thread's copy stream, ingest + forward + top-k + pack on
         its compute stream, D2H of the packed rows and of the per-cloud row offsets."""
         cur, cs = self.streams[t], self.copy_streams[t]
@@ -137,10 +135,9 @@ class Extractor:
         slot.host_off[: b + 1].copy_(p["local_offsets"], non_blocking=True)
         slot.done = torch.cuda.Event()
         slot.done.record(cur)
-        slot.gather_done = None
-        if self.comms is not None:                         # the ONE collective of the path, off the compute stream
-            from .parallel import on_side_stream
-            comm, g = self.comms[t], p["global"]
+        slot.gather_ticket = None
+        if self.comm is not None:                          # the ONE collective of the path: by the gather thread, in batch order
+            comm, g = self.comm, p["global"]
             if slot.host_all is None or slot.host_all.shape[0] < comm.world * b:
                 slot.host_all = torch.empty((comm.world * b, self.gdim), dtype=torch.float32).pin_memory()
 
@@ -151,7 +148,8 @@ class Extractor:
                 ev.record(torch.cuda.current_stream())
                 return ev
 
-            slot.gather_done = on_side_stream(self.comm_streams[t], gather, g)
+            self.gatherer.submit(seq, gather, g)
+            slot.gather_ticket = seq
         return slot, b
 
     def _finish(self, handle) -> Dict[str, torch.Tensor]:
@@ -161,9 +159,9 @@ class Extractor:
         k, g, d = self.topk, self.gdim, self.ddim
         off = slot.host_off[: b + 1]
         extra = {}
-        if slot.gather_done is not None:
-            slot.gather_done.synchronize()
-            extra["global_all"] = slot.host_all[: self.comms[0].world * b].clone()
+        if slot.gather_ticket is not None:
+            self.gatherer.result(slot.gather_ticket).synchronize()
+            extra["global_all"] = slot.host_all[: self.comm.world * b].clone()
         return {**extra, "global": out[:, :g].clone(), "keypoints": out[:, g:g + 3 * k].reshape(b, k, 3).clone(),
                 "descriptors": out[:, g + 3 * k:].reshape(b, k, d).clone(), "n_keypoints": (off[1:] - off[:-1]).clamp(max=k).clone()}
 
@@ -172,7 +170,10 @@ class Extractor:
         """Worker threads live as long as the extractor (started at the first extract(), stopped by close())."""
         if getattr(self, "_threads", None):
             return
-        self._works = [queue.Queue() for _ in range(self.S)]   # batch i goes to stream i % S (deterministic: collectives pair up)
+        self._works = [queue.Queue() for _ in range(self.S)]   # batch i goes to stream i % S
+        if self.comm is not None:
+            from .parallel import OrderedGatherer
+            self.gatherer = OrderedGatherer(self.device, first_ticket=getattr(self, "_seq_base", 0))
         self._done: Dict[int, object] = {}
         self._cond = threading.Condition()
 
@@ -206,8 +207,10 @@ class Extractor:
                     if item is not None:
                         seq, clouds = item
                         try:
-                            new = (seq, self._launch(t, self.slots[t][j & 1], clouds))
+                            new = (seq, self._launch(t, self.slots[t][j & 1], clouds, seq))
                         except BaseException as exc:       # delivered to the consumer in order
+                            if self.gatherer is not None and self.slots[t][j & 1].gather_ticket != seq:
+                                self.gatherer.submit(seq, None)   # a failed batch still releases the collectives after it
                             deliver(seq, exc)
                         j += 1
                     if pending is not None:
@@ -231,6 +234,9 @@ class Extractor:
             for th in self._threads:
                 th.join()
             self._threads = None
+            if self.gatherer is not None:
+                self.gatherer.close()
+                self.gatherer = None
 
     def __del__(self):
         try:

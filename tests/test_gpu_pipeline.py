@@ -64,3 +64,25 @@ def test_extractor_matches_direct_calls_in_order(cuda, weights):
     assert torch.equal(next(it)["global"], expect[0][0])
     with pytest.raises(Exception):
         next(it)
+
+
+def test_extractor_growing_batches_reallocate_staging_safely(cuda, weights):
+    """Regression: when a batch needs a larger device staging buffer, the caching allocator may hand the copy stream a block
+    that kernels still queued on the compute stream write (outputs of the previous batch, already freed on the host); the
+    extractor orders the copy stream behind the compute stream on (re)allocation.  Batches grow so that every slot
+    reallocates several times while work is in flight."""
+    import egonn_b200 as E
+    from egonn_b200 import synth
+    mp = E.ModelParams.from_dict(model="egonn", coordinates="cartesian", quantization_step=0.3)
+    model = E.model_factory(mp)
+    model.load_state_dict(weights)
+    model = model.eval().to(cuda)
+    sizes = [2000, 2500, 9000, 12000, 40000, 52000, 160000, 200000, 600000, 700000]
+    batches = [[synth.uniform_cloud(n, 10 + i)] for i, n in enumerate(sizes)]
+    expect = [_direct(model, b, 32, cuda)[0] for b in batches]
+    for rep in range(3):
+        ext = E.Extractor(model, streams=2, topk=32)                   # fresh slots: the growth happens again
+        got = [r["global"] for r in ext.extract(iter(batches))]
+        ext.close()
+        for i, (g, e) in enumerate(zip(got, expect)):
+            assert torch.equal(g, e), f"repetition {rep}, batch {i}"

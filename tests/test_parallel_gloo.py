@@ -4,6 +4,7 @@ because there is no GPU here; the GPU path of the same code runs under bench.py 
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -72,3 +73,114 @@ def test_sharded_batch_partition_and_imbalance():
     assert 1.0 <= shares[0].imbalance <= 1.1
     empty = ShardedBatch(clouds[:2], batched, 3, 4)                                     # more ranks than clouds
     assert empty.mine == [] and empty.coords is None
+
+
+def test_ordered_gatherer_issues_in_ticket_order_whatever_the_submission_order():
+    """Host logic of the multi-GPU collective path: worker threads submit in arbitrary order, ONE thread issues in ticket
+    order (the CUDA plumbing is replaced by no-ops here; NCCL itself runs in tests/test_gpu_multi.py)."""
+    import random
+    import threading
+    import time
+    from egonn_b200.parallel import OrderedGatherer
+
+    class CpuGatherer(OrderedGatherer):
+        def _make_stream(self):
+            return None
+
+        def _record_event(self):
+            return None
+
+        def _run_on_stream(self, ev, fn, tensors):
+            return fn()
+
+    issued = []
+    g = CpuGatherer(torch.device("cpu"), first_ticket=10)
+    n, S = 40, 4
+
+    def worker(t):
+        rnd = random.Random(t)
+        for i in range(10 + t, 10 + n, S):
+            time.sleep(rnd.random() * 0.003)
+            if i == 23:
+                g.submit(i, None)                               # a failed step still consumes its ticket
+            else:
+                g.submit(i, lambda i=i: issued.append(i) or i * 2)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(S)]
+    for th in threads:
+        th.start()
+    assert g.result(12) == 24                                   # waits for tickets 10, 11, 12
+    for th in threads:
+        th.join()
+    g.drain(10 + n)
+    assert issued == [i for i in range(10, 10 + n) if i != 23]
+    assert g.result(49) == 98 and g.result(23) is None
+    g.forget_results()
+    g.submit(50, lambda: (_ for _ in ()).throw(RuntimeError("boom")))
+    try:
+        g.drain(51)
+        raised = False
+    except RuntimeError:
+        raised = True
+    assert raised
+    g.close()
+
+
+def _ordered_worker(rank, world, port, out):
+    """Four worker threads per rank finish their steps in rank-dependent random order; every collective is a real (host
+    blocking) gloo all-gather issued by the rank's gather thread.  Any order mismatch between the ranks would pair up
+    tensors of different steps (caught below) or block for ever (caught by the timeout of the test)."""
+    import random
+    import threading
+    import time
+    from egonn_b200.parallel import OrderedGatherer
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class CpuGatherer(OrderedGatherer):
+        def _make_stream(self):
+            return None
+
+        def _record_event(self):
+            return None
+
+        def _run_on_stream(self, ev, fn, tensors):
+            return fn()
+
+    g = CpuGatherer(torch.device("cpu"))
+    n, S = 48, 4
+
+    def gather(i):
+        send = torch.tensor([[float(rank), float(i)]])
+        recv = torch.empty((world, 2))
+        dist.all_gather_into_tensor(recv, send)
+        return recv
+
+    def worker(t):
+        rnd = random.Random(1000 * rank + t)
+        for i in range(t, n, S):
+            time.sleep(rnd.random() * 0.004)                    # the ranks' threads drift apart
+            g.submit(i, lambda i=i: gather(i))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(S)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    g.drain(n)
+    ok = True
+    for i in range(n):
+        r = g.result(i)
+        ok = ok and r[:, 0].tolist() == [float(k) for k in range(world)] and r[:, 1].tolist() == [float(i)] * world
+    g.close()
+    if rank == 0:
+        torch.save(ok, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(240)
+def test_ordered_gatherer_pairs_up_collectives_across_two_ranks(tmp_path):
+    out = str(tmp_path / "ok.pt")
+    mp.spawn(_ordered_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.load(out) is True
