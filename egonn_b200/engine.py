@@ -84,6 +84,7 @@ class Engine:
         with torch.cuda.device(c.device):
             L.check(self.lib.egn_coords_build(self._ctx, _ptr(c), c.shape[0], C.byref(info), _stream()))
         self._coords_keepalive = c
+        self._derived = {}                                   # index tensors derived from the pyramid (egonn_b200.autograd)
         self.info = CoordsInfo(info.n_batches, info.n_input, list(info.n_rows))
         return self.info
 
@@ -102,6 +103,7 @@ class Engine:
             L.check(self.lib.egn_coords_build_points(self._ctx, _ptr(pts), pts.shape[0], _ptr(off), off.shape[0] - 1, cstep,
                                                      int(polar), C.byref(info), _stream()))
         self._coords_keepalive = (pts, off)
+        self._derived = {}
         self.info = CoordsInfo(info.n_batches, info.n_input, list(info.n_rows))
         return self.info
 

@@ -1,6 +1,8 @@
 """``MinkowskiEngine``-shaped front end of the CUDA engine: the ME symbols the reference touches
 (SURVEY.md §8b.2), each operator dispatched through the C ABI (``egn_conv``, ``egn_global_pool``,
 ``egn_broadcast_mul``, ``egn_quantize``, ``egn_coords_build``).  CUDA tensors only - no CPU path.
+With autograd enabled and a parameter or input that requires a gradient, the sparse operators go through
+``egonn_b200.autograd`` (backward = the engine's own forward operators on transposed kernels; training mode).
 
 Registering this package as ``MinkowskiEngine`` (``egonn_b200.minkowski.install()``) lets the reference's
 own ``models/*.py`` / ``layers/*.py`` run unmodified on the B200; ``egonn_b200.models`` uses the same
@@ -18,6 +20,7 @@ import torch
 import torch.nn as nn
 
 from ..engine import Engine
+from .. import autograd as _ag
 from .. import quantization as _q
 
 __version__ = "0.5.4-egonn_b200"
@@ -131,7 +134,10 @@ class MinkowskiConvolution(nn.Module):
 
     def forward(self, x: SparseTensor) -> SparseTensor:
         lvl = x.coordinate_map_key.level
-        f = x.coordinate_manager.conv(lvl, self.kernel_size, self._transposed, x.F, self.kernel)
+        if _ag.wants_grad(x.F, self.kernel):               # training (training/trainer.py:141-195): egonn_b200.autograd
+            f = _ag.SparseConvFunction.apply(x.F, self.kernel, x.coordinate_manager, lvl, self.kernel_size, self._transposed)
+        else:
+            f = x.coordinate_manager.conv(lvl, self.kernel_size, self._transposed, x.F, self.kernel)
         out = lvl if self.kernel_size != 2 else (lvl - 1 if self._transposed else lvl + 1)
         return SparseTensor(f, coordinate_manager=x.coordinate_manager, coordinate_map_key=CoordinateMapKey(out))
 
@@ -192,7 +198,10 @@ class MinkowskiGlobalPooling(nn.Module):
         super().__init__()
 
     def forward(self, x: SparseTensor) -> SparseTensor:
-        f = x.coordinate_manager.global_pool(x.coordinate_map_key.level, x.F, self._max)
+        if _ag.wants_grad(x.F):
+            f = _ag.GlobalPoolFunction.apply(x.F, x.coordinate_manager, x.coordinate_map_key.level, self._max)
+        else:
+            f = x.coordinate_manager.global_pool(x.coordinate_map_key.level, x.F, self._max)
         return SparseTensor(f, coordinate_manager=x.coordinate_manager, coordinate_map_key=CoordinateMapKey(0, origin=True))
 
 
@@ -215,6 +224,8 @@ class MinkowskiAvgPooling(nn.Module):
 
 class MinkowskiBroadcastMultiplication(nn.Module):
     def forward(self, x: SparseTensor, y: SparseTensor) -> SparseTensor:
+        if _ag.wants_grad(x.F, y.F):
+            return x._like(_ag.BroadcastMulFunction.apply(x.F, y.F, x.coordinate_manager, x.coordinate_map_key.level))
         return x._like(x.coordinate_manager.broadcast_mul(x.coordinate_map_key.level, x.F, y.F))
 
 

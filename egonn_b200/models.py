@@ -4,10 +4,13 @@ models/minkgl.py:228-315) and whose ``state_dict`` has the reference's key names
 (SURVEY.md Appendix B), so ``weights/model_egonn_20210916_1104.pth`` loads unchanged.
 
 Two execution paths share the parameters:
-  * ``forward``           - ONE ``egn_forward`` call: the whole network scheduled by the C++ engine.
+  * ``forward`` in ``eval()`` mode - ONE ``egn_forward`` call: the whole network scheduled by the C++ engine
+                            (eval-mode BatchNorm folded into the convolution epilogues).
   * ``forward_layerwise`` - the reference's layer-by-layer walk on ``egonn_b200.minkowski`` operators
-                            (each a C-ABI call); used to cross-check the fused path.
-Both are CUDA-only and inference-only (``model.eval()``; train-mode BatchNorm is out of scope).
+                            (each a C-ABI call); used to cross-check the fused path, and - with autograd enabled - it is
+                            what ``forward`` runs in ``train()`` mode: batch-statistics BatchNorm and gradients through
+                            ``egonn_b200.autograd`` (the training step of training/trainer.py:141-195).
+Both are CUDA-only.
 """
 from __future__ import annotations
 
@@ -311,7 +314,7 @@ class MinkGL(_EngineModel):
     def forward_packed(self, batch: Dict[str, torch.Tensor], disable_global_head=False, disable_local_head=False) -> Dict:
         """Same computation as ``forward`` but local outputs stay packed: (n,128)/(n,3)/(n,1) tensors in canonical
         row order + ``local_coords`` (n,4) + ``local_offsets`` (B+1) on the device - no per-cloud Python lists."""
-        assert not self.training, "egonn_b200 runs inference only: call model.eval()"
+        assert not self.training, "the fused path folds eval-mode BatchNorm: call model.eval() (train mode runs through forward())"
         coords, feats = batch["coords"], batch["features"]
         if not coords.is_cuda or not feats.is_cuda:
             raise RuntimeError("egonn_b200 has no CPU path: move batch['coords'] and batch['features'] to a CUDA device")
@@ -334,7 +337,7 @@ class MinkGL(_EngineModel):
         """Fused ingest + forward for the caller sequence of eval/evaluate.py:331-338: raw points of B clouds
         concatenated ((n,3) f32, CUDA) + first-point offsets ((B+1,) int32, CUDA) -> the packed outputs of
         ``forward_packed`` on the quantised, batched, all-ones-feature input - one sort, one host sync."""
-        assert not self.training, "egonn_b200 runs inference only: call model.eval()"
+        assert not self.training, "the fused path folds eval-mode BatchNorm: call model.eval() (train mode runs through forward())"
         if not points.is_cuda:
             raise RuntimeError("egonn_b200 has no CPU path: move the points to a CUDA device")
         eng = self._engine_for(points.device)
@@ -351,8 +354,13 @@ class MinkGL(_EngineModel):
         out["n_rows"] = info.n_rows
         return out
 
-    @torch.no_grad()
     def forward(self, batch: Dict[str, torch.Tensor], disable_global_head: bool = False, disable_local_head: bool = False):
+        if self.training:                                           # training/trainer.py:124-126,160-162: layer walk with autograd
+            return self._walk(batch, disable_global_head, disable_local_head)
+        with torch.no_grad():
+            return self._forward_eval(batch, disable_global_head, disable_local_head)
+
+    def _forward_eval(self, batch, disable_global_head, disable_local_head):
         p = self.forward_packed(batch, disable_global_head, disable_local_head)
         y = {}
         if "global" in p:
@@ -368,6 +376,12 @@ class MinkGL(_EngineModel):
     # -- reference-style layer walk (cross-check path) --------------------------------------------------------------
     @torch.no_grad()
     def forward_layerwise(self, batch, disable_global_head=False, disable_local_head=False):
+        return self._walk(batch, disable_global_head, disable_local_head)
+
+    def _walk(self, batch, disable_global_head=False, disable_local_head=False):
+        """models/minkgl.py:267-315 operator by operator; a new coordinate manager (engine context) per call, as
+        ``ME.SparseTensor(features, coordinates=...)`` creates one - several forwards may be alive before one backward
+        (training/trainer.py:178-188).  CPU tensors are rejected by the engine (no CPU path)."""
         x = ME.SparseTensor(batch["features"], coordinates=batch["coords"])
         x = self.trunk(x)
         y = {}
@@ -463,11 +477,14 @@ class _GlobalOnlyModel(_EngineModel):
     def _quant_desc(self):
         return self.quantizer.describe() if self.quantizer is not None else {"coordinates": "cartesian", "step": 1.0}
 
-    @torch.no_grad()
     def forward(self, batch, disable_local_head: bool = True):
         assert disable_local_head, "this model has only the global head"
-        assert not self.training, "egonn_b200 runs inference only: call model.eval()"
-        coords, feats = batch["coords"], batch["features"]
+        if self.training:                                           # layer walk with autograd (egonn_b200.autograd)
+            return self._walk(batch)
+        with torch.no_grad():
+            return self._forward_eval(batch["coords"], batch["features"])
+
+    def _forward_eval(self, coords, feats):
         if not coords.is_cuda or not feats.is_cuda:
             raise RuntimeError("egonn_b200 has no CPU path: move batch['coords'] and batch['features'] to a CUDA device")
         eng = self._engine_for(coords.device)
@@ -481,6 +498,9 @@ class _GlobalOnlyModel(_EngineModel):
 
     @torch.no_grad()
     def forward_layerwise(self, batch):
+        return self._walk(batch)
+
+    def _walk(self, batch):
         x = self.backbone(ME.SparseTensor(batch["features"], coordinates=batch["coords"]))
         return {"global": self.pooling(x)}
 
