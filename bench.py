@@ -201,15 +201,15 @@ def main():
     import egonn_b200 as E
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU path)"
 
-    def watchdog(phase):
+    def watchdog(phase, limit_s=300.0):
         """A phase that makes no progress for minutes (a collective whose peers never arrive) ends the process with every
         thread's traceback on stderr instead of hanging the box until the caller's limit."""
         faulthandler.cancel_dump_traceback_later()
         if phase is not None:
             print(f"[bench rank {rank}] {phase}", file=sys.stderr, flush=True)
-            faulthandler.dump_traceback_later(300 + 0.05 * args.steps, exit=True)
+            faulthandler.dump_traceback_later(limit_s + 0.05 * args.steps, exit=True)
 
-    watchdog("setup")
+    watchdog("setup", 600.0)                                  # workload synthesis (256 clouds with --strong), NCCL bring-up
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
