@@ -95,3 +95,54 @@ def test_sharded_extraction_two_gpus_nccl(tmp_path):
     res = torch.load(out)
     print("\n[2-GPU NCCL] gathered vs single-GPU global descriptors: rel err %.2e; voxels per rank %s" % (res["err"], res["loads"]))
     assert res["err"] <= 5e-5
+
+
+def _pipeline_worker(rank, world, port, out_path):
+    """The pipelined extractor with the collective (parallel.OrderedGatherer: one communicator, one communication stream,
+    batch order) on two GPUs: every rank extracts its own batches with two streams / host threads; ``global_all`` of batch i
+    must be the concatenation of both ranks' ``global`` of batch i, whatever the order in which the threads finish."""
+    import sys
+    sys.path.insert(0, REPO)
+    import torch.distributed as dist
+    import egonn_b200 as E
+    from egonn_b200 import parallel, synth
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    sd = torch.load(os.path.join(REPO, "tests", "golden", "egonn_weights.pth"), map_location="cpu", weights_only=True)
+    mp_ = E.ModelParams.from_dict(model="egonn", coordinates="cartesian", quantization_step=0.3)
+    model = E.model_factory(mp_)
+    model.load_state_dict(sd)
+    model = model.eval().to(dev)
+    comm = parallel.Communicator(dev)
+    # 9 batches of 2 clouds; sizes differ between the ranks and between batches, so the ranks' threads drift apart
+    batches = [[synth.uniform_cloud(2000 + 900 * ((i + 3 * rank) % 5), 100 * rank + 2 * i),
+                synth.uniform_cloud(1500 + 2500 * ((i + rank) % 3), 100 * rank + 2 * i + 1)] for i in range(9)]
+    ext = E.Extractor(model, streams=2, topk=32, device=dev, comm=comm)
+    mine, gathered = [], []
+    for res in ext.extract(iter(batches)):
+        mine.append(res["global"])
+        gathered.append(res["global_all"])
+    ext.close()
+    both = [torch.zeros((world * 2, 256), device=dev) for _ in batches]
+    for i, g in enumerate(mine):                                     # reference exchange through torch.distributed
+        dist.all_gather_into_tensor(both[i], g.to(dev).contiguous())
+    torch.cuda.synchronize()
+    worst = max(float((a - b.cpu()).abs().max()) for a, b in zip(gathered, both))
+    assert worst == 0.0, f"rank {rank}: global_all differs from the per-batch concatenation of the ranks' descriptors ({worst})"
+    if rank == 0:
+        torch.save({"batches": len(batches)}, out_path)
+    dist.barrier()
+    comm.close()
+    dist.destroy_process_group()
+
+
+def test_pipelined_extractor_with_collective_two_gpus_nccl(tmp_path):
+    """Not yet run on hardware when it was written (the round's GPU budget was spent): needs `gpurun --gpus 2`."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (run under `gpurun --gpus 2`)")
+    import torch.multiprocessing as mp
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_pipeline_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert torch.load(out)["batches"] == 9
