@@ -24,73 +24,6 @@ def cuda():
     return torch.device("cuda", 0)
 
 
-def test_training_step_matches_reference_autograd(cuda, weights):
-    import egonn_b200 as E
-    import train_case
-    mp = E.ModelParams.from_dict(model="egonn", coordinates="cartesian", quantization_step=train_case.QUANT["step"])
-    model = E.model_factory(mp)
-    model.load_state_dict(weights)
-    model = model.to(cuda)
-    coords = torch.from_numpy(load_golden("mini3_cartesian")["coords"]).to(cuda)
-    batch = train_case.batches(coords)[0]
-
-    before = model.eval()(batch)["global"].clone()                  # fused path, checkpoint weights
-    loss = train_case.step(model, coords)                           # train(): layer walk + egonn_b200.autograd
-    torch.cuda.synchronize()
-    golden = dict(np.load(os.path.join(GOLDEN, "train_mini3.npz")))
-    r = train_case.compare(model, loss, golden, 5e-2, 1e-3, 1e-4, "CUDA engine")     # bars: see train_case.compare
-    print("\n[training step, CUDA engine] loss %.6f (fixture %.6f); gradients: worst %s %.2e, median %.2e; forward: worst %s %.2e"
-          % (loss, float(golden["loss"]), *r["worst_grad"], r["median_grad"], *r["worst_forward"]))
-
-    # optimizer step, then inference again: the fused path must pick up the new parameters and running statistics
-    opt = torch.optim.SGD(model.parameters(), lr=1e-7)          # gradients reach 4e3 with this loss: a small, finite update
-    opt.step()
-    after = model.eval()(batch)["global"]
-    walk = model.forward_layerwise(batch)["global"]
-    torch.cuda.synchronize()
-    assert torch.isfinite(after).all()
-    assert float((after - before).abs().max()) > 0.0, "the fused path still runs the old weights"
-    assert float((after - walk).abs().max()) <= 1e-4 * float(walk.abs().max()), "fused path != layer walk after the update"
-
-
-def test_minkloc_training_step_engine_vs_cpu_double(cuda, monkeypatch):
-    import egonn_b200 as E
-    import egonn_b200.minkowski as ME
-    from cpu_engine import CpuEngine
-    torch.manual_seed(3)
-    mp = E.ModelParams.from_dict(model="MinkLoc", coordinates="cartesian", quantization_step=0.4, block="BasicBlock",
-                                 pooling="SPoC", feature_size=256, output_dim=256)
-    ref = E.model_factory(mp)
-    with torch.no_grad():
-        for name, b in ref.named_buffers():
-            if name.endswith("running_var"):
-                b.uniform_(0.5, 1.5)
-    model = copy.deepcopy(ref).to(cuda)
-    coords = torch.from_numpy(load_golden("mini3_cartesian")["coords"])
-
-    def step(m, c):
-        m.train()
-        m.zero_grad(set_to_none=True)
-        g = m({"coords": c, "features": torch.ones((c.shape[0], 1), device=c.device)})["global"]
-        loss = (g ** 2).sum() + g.sum()
-        loss.backward()
-        return float(loss.detach())
-
-    loss_gpu = step(model, coords.to(cuda))
-    torch.cuda.synchronize()
-    monkeypatch.setattr(ME, "Engine", CpuEngine)                    # same model classes, engine replaced by the oracle-backed double
-    loss_cpu = step(ref, coords)
-    assert abs(loss_gpu - loss_cpu) <= 1e-4 * abs(loss_cpu)
-    errs = {}
-    for (name, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
-        assert p.grad is not None and q.grad is not None, name
-        errs[name] = float((p.grad.cpu() - q.grad).abs().max()) / max(float(q.grad.abs().max()), 1e-30)
-    worst = max(errs.items(), key=lambda t: t[1])
-    median = float(np.median(list(errs.values())))
-    print("\n[MinkLoc training step] engine vs CPU double: worst %s %.2e, median %.2e" % (*worst, median))
-    assert worst[1] <= 5e-2 and median <= 1e-3, (worst, median)     # two bars: see train_case.compare
-
-
 def _lex(c: torch.Tensor) -> torch.Tensor:
     """Row order that sorts (N,4) coordinates lexicographically: engine and double are compared keyed by coordinate."""
     c = c.cpu().long()
@@ -168,3 +101,70 @@ def test_pool_and_broadcast_backward_rules_on_the_engine(cuda, is_max):
     gx2r, gg2r = torch.autograd.grad(xr * gr[bidx], [xr, gr], gy2)
     assert float((gx2 - gx2r).abs().max()) <= 1e-5 * float(gx2r.abs().max())
     assert float((gg2 - gg2r).abs().max()) <= 1e-4 * float(gg2r.abs().max())
+
+
+def test_training_step_matches_reference_autograd(cuda, weights):
+    import egonn_b200 as E
+    import train_case
+    mp = E.ModelParams.from_dict(model="egonn", coordinates="cartesian", quantization_step=train_case.QUANT["step"])
+    model = E.model_factory(mp)
+    model.load_state_dict(weights)
+    model = model.to(cuda)
+    coords = torch.from_numpy(load_golden("mini3_cartesian")["coords"]).to(cuda)
+    batch = train_case.batches(coords)[0]
+
+    before = model.eval()(batch)["global"].clone()                  # fused path, checkpoint weights
+    loss = train_case.step(model, coords)                           # train(): layer walk + egonn_b200.autograd
+    torch.cuda.synchronize()
+    golden = dict(np.load(os.path.join(GOLDEN, "train_mini3.npz")))
+    r = train_case.compare(model, loss, golden, 5e-2, 1e-3, 1e-4, "CUDA engine")     # bars: see train_case.compare
+    print("\n[training step, CUDA engine] loss %.6f (fixture %.6f); gradients: worst %s %.2e, median %.2e; forward: worst %s %.2e"
+          % (loss, float(golden["loss"]), *r["worst_grad"], r["median_grad"], *r["worst_forward"]))
+
+    # optimizer step, then inference again: the fused path must pick up the new parameters and running statistics
+    opt = torch.optim.SGD(model.parameters(), lr=1e-7)          # gradients reach 4e3 with this loss: a small, finite update
+    opt.step()
+    after = model.eval()(batch)["global"]
+    walk = model.forward_layerwise(batch)["global"]
+    torch.cuda.synchronize()
+    assert torch.isfinite(after).all()
+    assert float((after - before).abs().max()) > 0.0, "the fused path still runs the old weights"
+    assert float((after - walk).abs().max()) <= 1e-4 * float(walk.abs().max()), "fused path != layer walk after the update"
+
+
+def test_minkloc_training_step_engine_vs_cpu_double(cuda, monkeypatch):
+    import egonn_b200 as E
+    import egonn_b200.minkowski as ME
+    from cpu_engine import CpuEngine
+    torch.manual_seed(3)
+    mp = E.ModelParams.from_dict(model="MinkLoc", coordinates="cartesian", quantization_step=0.4, block="BasicBlock",
+                                 pooling="SPoC", feature_size=256, output_dim=256)
+    ref = E.model_factory(mp)
+    with torch.no_grad():
+        for name, b in ref.named_buffers():
+            if name.endswith("running_var"):
+                b.uniform_(0.5, 1.5)
+    model = copy.deepcopy(ref).to(cuda)
+    coords = torch.from_numpy(load_golden("mini3_cartesian")["coords"])
+
+    def step(m, c):
+        m.train()
+        m.zero_grad(set_to_none=True)
+        g = m({"coords": c, "features": torch.ones((c.shape[0], 1), device=c.device)})["global"]
+        loss = (g ** 2).sum() + g.sum()
+        loss.backward()
+        return float(loss.detach())
+
+    loss_gpu = step(model, coords.to(cuda))
+    torch.cuda.synchronize()
+    monkeypatch.setattr(ME, "Engine", CpuEngine)                    # same model classes, engine replaced by the oracle-backed double
+    loss_cpu = step(ref, coords)
+    assert abs(loss_gpu - loss_cpu) <= 1e-4 * abs(loss_cpu)
+    errs = {}
+    for (name, p), (_, q) in zip(model.named_parameters(), ref.named_parameters()):
+        assert p.grad is not None and q.grad is not None, name
+        errs[name] = float((p.grad.cpu() - q.grad).abs().max()) / max(float(q.grad.abs().max()), 1e-30)
+    worst = max(errs.items(), key=lambda t: t[1])
+    median = float(np.median(list(errs.values())))
+    print("\n[MinkLoc training step] engine vs CPU double: worst %s %.2e, median %.2e" % (*worst, median))
+    assert worst[1] <= 5e-2 and median <= 1e-3, (worst, median)     # two bars: see train_case.compare
