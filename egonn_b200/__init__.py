@@ -6,8 +6,10 @@
     model.load_state_dict(torch.load("weights.pth"))
     y = model({"coords": coords_cuda_int32_N4, "features": ones_cuda_N1})
 
-Everything that computes runs in hand-written sm_100a CUDA kernels behind the C ABI of
-``include/egonn_b200.h`` (``egonn_b200/csrc/libegonn_b200.so``).  There is no CPU fallback.
+The inference path (``model.eval()``) runs entirely in hand-written sm_100a CUDA kernels behind the C ABI of
+``include/egonn_b200.h`` (``egonn_b200/csrc/libegonn_b200.so``).  The training step (``model.train()``) walks
+the layers on the same C-ABI operators, with torch's BatchNorm / Linear on the feature matrices and torch's GEMM for the
+weight gradients (``egonn_b200.autograd``).  There is no CPU fallback.
 """
 from .params import ModelParams  # noqa: F401
 from .models import (model_factory, create_egonn_model, MinkGL, MinkTrunk, MinkHead, ECABasicBlock, MinkFPN,  # noqa: F401
