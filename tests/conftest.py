@@ -41,3 +41,17 @@ GOLDEN_CASES = {
     "mini3_cartesian": dict(coordinates="cartesian", step=0.4),
     "mini2_polar": dict(coordinates="polar", step=[1., 0.3, 0.2]),
 }
+# Fixtures written by the REAL MinkowskiEngine (tools/verify_against_me.py --write-golden, on a machine that has ME 0.5.4)
+# join the golden cases of every CPU (oracle) and GPU (engine) parity test as soon as they are committed: <case>_me.npz.
+# None exist yet - MinkowskiEngine cannot be installed in this image - so the oracle's ME semantics stay "parity unpinned".
+for _case in list(GOLDEN_CASES):
+    if os.path.exists(os.path.join(GOLDEN, _case + "_me.npz")):
+        GOLDEN_CASES[_case + "_me"] = GOLDEN_CASES[_case]
+
+
+def train_fixtures():
+    """Training-step fixtures: the shim-generated one, plus the real-ME one when it has been committed."""
+    names = ["train_mini3.npz"]
+    if os.path.exists(os.path.join(GOLDEN, "train_mini3_me.npz")):
+        names.append("train_mini3_me.npz")
+    return names

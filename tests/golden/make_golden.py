@@ -40,15 +40,40 @@ CASES = {
 }
 
 
-def main():
-    ref_import.enable()
+def enable_real_me(reference_root: str):
+    """The reference on the REAL MinkowskiEngine (tools/verify_against_me.py --write-golden, on a machine that has it):
+    same import work-arounds as oracle/ref_import.py, without the shim."""
+    import types
+    import MinkowskiEngine as ME
+    assert "oracle" not in getattr(ME, "__version__", "") and "egonn_b200" not in getattr(ME, "__version__", ""), \
+        "this must be the real MinkowskiEngine"
+    if reference_root not in sys.path:
+        sys.path.insert(0, reference_root)
+    m = types.ModuleType("datasets")                                   # HuggingFace `datasets` shadows the reference's package
+    m.__path__ = [os.path.join(reference_root, "datasets")]
+    sys.modules["datasets"] = m
+
+
+def main(real_me: bool = False, reference_root: str = None, suffix: str = ""):
+    """``real_me``: run on the real MinkowskiEngine and write ``<case><suffix>.npz`` (suffix "_me"): the fixtures that PIN the
+    oracle - tests/conftest.py adds every ``<case>_me.npz`` it finds to the golden cases of the CPU and GPU parity tests."""
+    if real_me:
+        enable_real_me(reference_root or ref_import.REFERENCE_ROOT)
+    else:
+        ref_import.enable()
     import MinkowskiEngine as ME
     from models.model_factory import model_factory
     from misc.utils import ModelParams
 
-    sd = torch.load(os.path.join(ref_import.REFERENCE_ROOT, "weights", "model_egonn_20210916_1104.pth"),
-                    map_location="cpu", weights_only=True)
-    torch.save({k: v.clone() for k, v in sd.items()}, os.path.join(HERE, "egonn_weights.pth"))
+    if real_me:
+        sd = torch.load(os.path.join(HERE, "egonn_weights.pth"), map_location="cpu", weights_only=True)
+    else:
+        sd = torch.load(os.path.join(ref_import.REFERENCE_ROOT, "weights", "model_egonn_20210916_1104.pth"),
+                        map_location="cpu", weights_only=True)
+        torch.save({k: v.clone() for k, v in sd.items()}, os.path.join(HERE, "egonn_weights.pth"))
+
+    def to_np(t):
+        return t.detach().cpu().numpy().copy()
 
     for name, (coordinates, step, make) in CASES.items():
         with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
@@ -64,14 +89,14 @@ def main():
         for pc in clouds:
             c, ndx = mp.quantizer(torch.from_numpy(pc))           # eval/evaluate.py:331
             coords.append(c)
-            index.append(ndx.numpy())
+            index.append(to_np(ndx))
         bcoords = ME.utils.batched_coordinates(coords)             # eval/evaluate.py:333
         feats = torch.ones((bcoords.shape[0], 1), dtype=torch.float32)
 
         grabbed = {}
         def grab(key):
             def hook(_m, _i, o):
-                grabbed[key] = (o.C.numpy().copy(), o.F.detach().numpy().copy())
+                grabbed[key] = (to_np(o.C).astype(np.int32), to_np(o.F))
             return hook
         handles = [model.local_keypoint_regressor.register_forward_hook(grab("kp"))]
         for L in range(1, 8):
@@ -85,7 +110,7 @@ def main():
         order = me_ops.canonical_order(c3)
         # the reference returns per-cloud lists in map row order; concatenate in batch order and
         # re-sort canonically (rows of one cloud are contiguous in both orders)
-        cat = lambda lst: torch.cat(lst, dim=0).numpy()
+        cat = lambda lst: to_np(torch.cat(lst, dim=0))
         rows = np.concatenate(me_ops.batch_rows(c3))
         inv = np.empty_like(rows)
         inv[rows] = np.arange(rows.shape[0])
@@ -94,8 +119,8 @@ def main():
             "points": np.concatenate(clouds, axis=0),
             "points_splits": np.cumsum([0] + [p.shape[0] for p in clouds]),
             "quant_index": np.concatenate(index),
-            "coords": bcoords.numpy(),
-            "global": y["global"].numpy(),
+            "coords": to_np(bcoords).astype(np.int32),
+            "global": to_np(y["global"]),
             "coords_L3": c3[order],
             "descriptors": cat(y["descriptors"])[inv][order],
             "keypoints": cat(y["keypoints"])[inv][order],
@@ -107,7 +132,7 @@ def main():
             out[f"coords_L{L}"] = cL[o]
             if L in (1, 3, 5, 7):
                 out[f"block{L}"] = fL[o]
-        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        np.savez_compressed(os.path.join(HERE, name + suffix + ".npz"), **out)
         print(name, "points", out["points"].shape, "voxels", bcoords.shape[0],
               "levels", [out[f'coords_L{L}'].shape[0] for L in range(1, 8)], "global[0,:3]", out["global"][0, :3])
 

@@ -18,13 +18,20 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, REPO)
 sys.path.insert(0, os.path.join(REPO, "tests"))
+sys.path.insert(0, HERE)
 
 from oracle import ref_import  # noqa: E402
 import train_case  # noqa: E402
 
 
-def main():
-    ref_import.enable()
+def main(real_me: bool = False, reference_root: str = None, suffix: str = ""):
+    """``real_me`` (tools/verify_against_me.py --write-golden): the same step on the REAL MinkowskiEngine ->
+    ``train_mini3_me.npz``, which the training tests then check as well."""
+    if real_me:
+        import make_golden
+        make_golden.enable_real_me(reference_root or ref_import.REFERENCE_ROOT)
+    else:
+        ref_import.enable()
     from models.model_factory import model_factory
     from misc.utils import ModelParams
     sd = torch.load(os.path.join(HERE, "egonn_weights.pth"), map_location="cpu", weights_only=True)
@@ -38,8 +45,9 @@ def main():
     torch.manual_seed(0)
     loss = train_case.step(model, coords)
     rec = train_case.record(model, loss)
-    np.savez_compressed(os.path.join(HERE, "train_mini3.npz"), **rec)
-    print("loss", loss, "tensors", len(rec), "bytes", os.path.getsize(os.path.join(HERE, "train_mini3.npz")))
+    path = os.path.join(HERE, "train_mini3" + suffix + ".npz")
+    np.savez_compressed(path, **rec)
+    print("loss", loss, "tensors", len(rec), "bytes", os.path.getsize(path))
 
 
 if __name__ == "__main__":

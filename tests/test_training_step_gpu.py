@@ -13,7 +13,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN, load_golden
+from conftest import GOLDEN, load_golden, train_fixtures
 
 pytestmark = pytest.mark.gpu
 
@@ -116,10 +116,11 @@ def test_training_step_matches_reference_autograd(cuda, weights):
     before = model.eval()(batch)["global"].clone()                  # fused path, checkpoint weights
     loss = train_case.step(model, coords)                           # train(): layer walk + egonn_b200.autograd
     torch.cuda.synchronize()
-    golden = dict(np.load(os.path.join(GOLDEN, "train_mini3.npz")))
-    r = train_case.compare(model, loss, golden, 5e-2, 1e-3, 1e-4, "CUDA engine")     # bars: see train_case.compare
-    print("\n[training step, CUDA engine] loss %.6f (fixture %.6f); gradients: worst %s %.2e, median %.2e; forward: worst %s %.2e"
-          % (loss, float(golden["loss"]), *r["worst_grad"], r["median_grad"], *r["worst_forward"]))
+    for fixture in train_fixtures():                                # + the real-MinkowskiEngine fixture once it exists
+        golden = dict(np.load(os.path.join(GOLDEN, fixture)))
+        r = train_case.compare(model, loss, golden, 5e-2, 1e-3, 1e-4, f"CUDA engine vs {fixture}")     # bars: see train_case.compare
+        print("\n[training step, CUDA engine vs %s] loss %.6f (fixture %.6f); gradients: worst %s %.2e, median %.2e; forward: worst %s %.2e"
+              % (fixture, loss, float(golden["loss"]), *r["worst_grad"], r["median_grad"], *r["worst_forward"]))
 
     # optimizer step, then inference again: the fused path must pick up the new parameters and running statistics
     opt = torch.optim.SGD(model.parameters(), lr=1e-7)          # gradients reach 4e3 with this loss: a small, finite update

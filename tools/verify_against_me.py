@@ -6,6 +6,13 @@ NOT runnable in the build image or on the B200 boxes (MinkowskiEngine is not ins
 tests/golden/make_golden.py and prints the maximum relative differences, keyed by coordinate.
 
     PYTHONPATH=/path/to/Egonn python tools/verify_against_me.py --reference /path/to/Egonn [--gpu]
+    python tools/verify_against_me.py --reference /path/to/Egonn --write-golden
+
+--write-golden writes the fixtures that PIN the oracle: the three golden cases of tests/golden/make_golden.py and the
+training step of tests/golden/make_golden_train.py, produced by the reference's own model code on the REAL
+MinkowskiEngine, as tests/golden/<case>_me.npz and tests/golden/train_mini3_me.npz.  Commit them: tests/conftest.py adds
+every <case>_me.npz to the golden cases of the CPU (oracle) and GPU (engine) parity tests, and the training tests check
+train_mini3_me.npz next to the shim-generated fixture.
 """
 import argparse
 import os
@@ -24,7 +31,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", required=True)
     ap.add_argument("--gpu", action="store_true", help="also run the egonn_b200 engine")
+    ap.add_argument("--write-golden", action="store_true", help="write tests/golden/*_me.npz from the real MinkowskiEngine and exit")
     args = ap.parse_args()
+    if args.write_golden:
+        sys.path.insert(0, os.path.join(REPO, "tests", "golden"))
+        sys.path.insert(0, os.path.join(REPO, "tests"))
+        import make_golden
+        import make_golden_train
+        make_golden.main(real_me=True, reference_root=args.reference, suffix="_me")
+        make_golden_train.main(real_me=True, reference_root=args.reference, suffix="_me")
+        print("wrote tests/golden/*_me.npz - run `python -m pytest tests -m 'not gpu'` (and -m gpu on a B200) and commit them")
+        return
     import MinkowskiEngine as ME                                       # the real one
     assert "oracle" not in getattr(ME, "__version__", ""), "this must be the real MinkowskiEngine"
     sys.path.insert(0, args.reference)
