@@ -1,5 +1,6 @@
 import os
 import sys
+import types
 
 import pytest
 
@@ -55,3 +56,38 @@ def train_fixtures():
     if os.path.exists(os.path.join(GOLDEN, "train_mini3_me.npz")):
         names.append("train_mini3_me.npz")
     return names
+
+
+REF_ROOT = os.environ.get("EGONN_REFERENCE_ROOT", "/root/reference")
+TOPS = ("MinkowskiEngine", "models", "layers", "misc", "datasets")
+
+
+@pytest.fixture()
+def reference_on_front_end(monkeypatch):
+    """model_factory / ModelParams of the unmodified reference on the egonn_b200 front end + CPU double; sys.modules and
+    sys.path are restored afterwards (other tests import the reference on the ORACLE shim)."""
+    if not os.path.isdir(os.path.join(REF_ROOT, "models")):
+        pytest.skip("reference sources absent")
+    import egonn_b200.minkowski as front
+    from cpu_engine import CpuEngine
+    monkeypatch.setattr(front, "Engine", CpuEngine)
+    saved = {n: m for n, m in sys.modules.items() if n.split(".")[0] in TOPS}
+    saved_path = list(sys.path)
+    for n in saved:
+        del sys.modules[n]
+    front.install()
+    sys.path.insert(0, REF_ROOT)
+    m = types.ModuleType("datasets")                                   # HuggingFace `datasets` shadows the reference's package
+    m.__path__ = [os.path.join(REF_ROOT, "datasets")]
+    sys.modules["datasets"] = m
+    from misc.utils import ModelParams
+    from models.model_factory import model_factory
+    import models.minkgl
+    assert models.minkgl.__file__.startswith(REF_ROOT) and sys.modules["MinkowskiEngine"] is front
+    try:
+        yield model_factory, ModelParams
+    finally:
+        for n in [n for n in sys.modules if n.split(".")[0] in TOPS]:
+            del sys.modules[n]
+        sys.modules.update(saved)
+        sys.path[:] = saved_path

@@ -128,45 +128,20 @@ def test_eval_mode_still_takes_the_fused_path(weights):
         model.train()({"coords": coords, "features": torch.ones((coords.shape[0], 1))})     # the real engine refuses CPU too
 
 
-def test_unmodified_reference_graph_trains_on_the_front_end(cpu_engine, weights):
+def test_unmodified_reference_graph_trains_on_the_front_end(reference_on_front_end, weights):
     """INTEGRATION.md path 2 in training mode: the reference's OWN ``models/model_factory.py`` / ``models/minkgl.py`` /
     ``layers/*.py`` (imported unmodified from /root/reference, skipped where it is absent) on ``egonn_b200.minkowski``
     registered as ``MinkowskiEngine`` - engine replaced by the CPU double here - gives the fixture's gradients."""
-    import sys
     import tempfile
-    import types
     import train_case
-    ref_root = os.environ.get("EGONN_REFERENCE_ROOT", "/root/reference")
-    if not os.path.isdir(os.path.join(ref_root, "models")):
-        pytest.skip("reference sources absent")
-    import egonn_b200.minkowski as front
-    tops = ("MinkowskiEngine", "models", "layers", "misc", "datasets")
-    saved = {n: m for n, m in sys.modules.items() if n.split(".")[0] in tops}
-    saved_path = list(sys.path)
-    try:
-        for n in saved:
-            del sys.modules[n]
-        front.install()
-        sys.path.insert(0, ref_root)
-        m = types.ModuleType("datasets")                               # HuggingFace `datasets` shadows the reference's package
-        m.__path__ = [os.path.join(ref_root, "datasets")]
-        sys.modules["datasets"] = m
-        from misc.utils import ModelParams                             # reference, unmodified
-        from models.model_factory import model_factory                 # reference, unmodified
-        import models.minkgl
-        assert models.minkgl.__file__.startswith(ref_root) and sys.modules["MinkowskiEngine"] is front
-        with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
-            f.write("[MODEL]\nmodel = egonn\ncoordinates = cartesian\nquantization_step = %s\n" % train_case.QUANT["step"])
-        model = model_factory(ModelParams(f.name))
-        os.unlink(f.name)
-        model.load_state_dict(weights)
-        coords = torch.from_numpy(load_golden("mini3_cartesian")["coords"])
-        loss = train_case.step(model, coords)
-        golden = dict(np.load(os.path.join(GOLDEN, "train_mini3.npz")))
-        r = train_case.compare(model, loss, golden, 2e-4, 2e-5, 1e-5, "reference graph on the front end (CPU double)")
-        print("\n[reference graph, front end + CPU double] gradients: worst %s %.2e" % r["worst_grad"])
-    finally:
-        for n in [n for n in sys.modules if n.split(".")[0] in tops]:
-            del sys.modules[n]
-        sys.modules.update(saved)
-        sys.path[:] = saved_path
+    model_factory, ModelParams = reference_on_front_end
+    with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+        f.write("[MODEL]\nmodel = egonn\ncoordinates = cartesian\nquantization_step = %s\n" % train_case.QUANT["step"])
+    model = model_factory(ModelParams(f.name))
+    os.unlink(f.name)
+    model.load_state_dict(weights)
+    coords = torch.from_numpy(load_golden("mini3_cartesian")["coords"])
+    loss = train_case.step(model, coords)
+    golden = dict(np.load(os.path.join(GOLDEN, "train_mini3.npz")))
+    r = train_case.compare(model, loss, golden, 2e-4, 2e-5, 1e-5, "reference graph on the front end (CPU double)")
+    print("\n[reference graph, front end + CPU double] gradients: worst %s %.2e" % r["worst_grad"])
