@@ -184,3 +184,67 @@ def test_ordered_gatherer_pairs_up_collectives_across_two_ranks(tmp_path):
     out = str(tmp_path / "ok.pt")
     mp.spawn(_ordered_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert torch.load(out) is True
+
+
+def test_ordered_gatherer_default_cuda_plumbing_with_a_fake_torch_cuda(monkeypatch):
+    """Every line of the DEFAULT plumbing (stream creation, event hand-over, collective issued under the communication
+    stream, record_stream of the inputs) executed against a recording stand-in of ``torch.cuda`` - there is no GPU here; the
+    real thing runs under ``bench.py --gpus N`` and tests/test_gpu_multi.py."""
+    import contextlib
+    import threading
+    from egonn_b200 import parallel
+    log, state = [], threading.local()
+
+    class FakeStream:
+        def __init__(self, name):
+            self.name = name
+
+        def wait_event(self, ev):
+            log.append(("wait", self.name, ev.recorded_on))
+
+    class FakeEvent:
+        recorded_on = None
+
+        def record(self, stream):
+            self.recorded_on = stream.name
+
+    class FakeTensor:
+        def __init__(self):
+            self.streams = []
+
+        def record_stream(self, s):
+            self.streams.append(s.name)
+
+    @contextlib.contextmanager
+    def fake_stream_ctx(s):
+        prev = getattr(state, "cur", None)
+        state.cur = s
+        try:
+            yield
+        finally:
+            state.cur = prev
+
+    monkeypatch.setattr(torch.cuda, "Stream", lambda device=None: FakeStream("comm"))
+    monkeypatch.setattr(torch.cuda, "Event", FakeEvent)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "stream", fake_stream_ctx)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda d=None: getattr(state, "cur", None) or FakeStream("default"))
+
+    g = parallel.OrderedGatherer(torch.device("cuda", 0))
+    tensors = [FakeTensor() for _ in range(6)]
+
+    def worker(t):
+        with torch.cuda.stream(FakeStream(f"compute{t}")):
+            for i in range(t, 6, 2):
+                g.submit(i, lambda i=i: (torch.cuda.current_stream().name, i), tensors[i])
+
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(2)]
+    for th in ths:
+        th.start()
+    for th in ths:
+        th.join()
+    g.drain(6)
+    assert [g.result(i) for i in range(6)] == [("comm", i) for i in range(6)]          # issued on the communication stream, in order
+    assert [e for e in log if e[0] == "wait"] == [("wait", "comm", f"compute{i % 2}") for i in range(6)]   # behind the step's event
+    assert all(t.streams == ["comm"] for t in tensors)
+    g.close()
